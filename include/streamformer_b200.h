@@ -1,0 +1,163 @@
+/* streamformer_b200.h — C ABI of the B200-native StreamFormer video-encoder hot path.
+ *
+ * The reference (Go2Heart/StreamFormer) has no FFI on this path: the boundary is the Python class
+ * TimesformerMultiTaskingModelSigLIP (models/modeling_timesformer_siglip.py:1241-1354) and its
+ * KV-cache twin (downstream/VideoQA/llava/model/multimodal_encoder/timesformer_encoder.py:1255-1392).
+ * This header is what that class binds instead of its eager torch ops: plain C, raw device pointers,
+ * sizes and a cudaStream_t; no ATen / pybind types.  The ctypes stub that binds it lives in
+ * streamformer_b200/_native.py and is reproduced in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative sf_status; sf_last_error() returns a
+ *    thread-local message describing the last failure;
+ *  - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *    nothing synchronises the host and nothing allocates inside sf_forward*/sf_layer_forward;
+ *  - a context is bound to one device and is NOT thread-safe (same as the reference: one model
+ *    replica per process / GPU);
+ *  - activations are bf16 or fp16 (sf_config.dtype); residual stream rows are ordered (b, n, t)
+ *    exactly like the reference's hidden_states [B, N*T, D] (…siglip.py:452-454).
+ */
+#ifndef STREAMFORMER_B200_H_
+#define STREAMFORMER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sf_status {
+  SF_OK = 0,
+  SF_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  SF_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed */
+  SF_ERR_DRIVER = -3,    /* tensor-map encode / driver entry point failure */
+  SF_ERR_STATE = -4,     /* weights not bound, cache overflow, ... */
+  SF_ERR_WORKSPACE = -5  /* caller-provided workspace too small */
+} sf_status;
+
+typedef enum sf_dtype { SF_BF16 = 0, SF_F16 = 1, SF_F32 = 2 } sf_dtype;
+typedef enum sf_act { SF_ACT_NONE = 0, SF_ACT_GELU = 1, SF_ACT_GELU_TANH = 2 } sf_act;
+typedef enum sf_rowmap { SF_ROW_IDENTITY = 0, SF_ROW_BTN_TO_BNT = 1, SF_ROW_BNT_TO_BTN = 2 } sf_rowmap;
+
+/* Mirrors StreamformerConfig (models/configuration_streamformer.py:92-137). */
+typedef struct sf_config {
+  int image_size;            /* 224 */
+  int patch_size;            /* 16  */
+  int num_channels;          /* 3   */
+  int num_frames;            /* rows of embeddings.time_embeddings (16) */
+  int hidden_size;           /* 768 */
+  int num_hidden_layers;     /* 12  */
+  int num_attention_heads;   /* 12 (head dim must be 64) */
+  int intermediate_size;     /* 3072 */
+  int hidden_act;            /* sf_act: SF_ACT_GELU ("gelu", erf) or SF_ACT_GELU_TANH */
+  float layer_norm_eps;      /* 1e-6 */
+  int causal_temporal;       /* config.enable_causal_temporal */
+  int dtype;                 /* sf_dtype of activations and packed matrices: SF_BF16 or SF_F16 */
+  int fold_temporal_proj;    /* 1: pre-multiply temporal_dense . temporal_attention.output.dense */
+} sf_config;
+
+/* One reference state-dict tensor (names exactly as in SURVEY.md 8(b), without any
+ * "timesformer." prefix). Pointers are BORROWED for the duration of sf_bind_weights only: the
+ * library packs (casts, merges LoRA, folds) into context-owned memory. */
+typedef struct sf_weight_desc {
+  const char* name;
+  const void* data;   /* device pointer */
+  int dtype;          /* sf_dtype */
+  int ndim;
+  int64_t shape[4];
+} sf_weight_desc;
+
+typedef struct sf_ctx sf_ctx;
+typedef struct sf_kv sf_kv;
+
+const char* sf_last_error(void);
+const char* sf_version(void);
+/* kernels launched by this library since it was loaded */
+uint64_t sf_launch_count(void);
+
+/* ---- model lifetime ---------------------------------------------------------------------- */
+/* replaces TimesformerMultiTaskingModelSigLIP.__init__ (…siglip.py:1244-1258) */
+int sf_create(const sf_config* cfg, int device, sf_ctx** out);
+int sf_destroy(sf_ctx* ctx);
+/* replaces load_state_dict / from_pretrained weight materialisation; may be called again after an
+ * optimiser step to re-pack. Optional LoRA tensors (…qkv_lora_{a,b}.weight, …dense_lora_{a,b}.weight,
+ * …siglip.py:632-647, 731-746) are merged W + B.A. */
+int sf_bind_weights(sf_ctx* ctx, void* stream, const sf_weight_desc* w, int n);
+/* interpolated position table for a non-default resolution (…siglip.py:380-411): fp32 [S, D] */
+int sf_set_pos_embed(sf_ctx* ctx, void* stream, const float* pos, int S);
+
+/* ---- full forward ------------------------------------------------------------------------ */
+int sf_workspace_bytes(const sf_ctx* ctx, int B, int T, int H, int W, size_t* out);
+/* replaces TimesformerMultiTaskingModelSigLIP.forward (…siglip.py:1299-1354).
+ *   pixels        [B, T, C, H, W], pixels_dtype in {bf16, f16, f32}
+ *   last_hidden   [B, T, S, D]  activation dtype            (last_hidden_state)
+ *   pooler        [B, T, D]     activation dtype            (pooler_output)
+ *   hidden_states NULL or L+1 device pointers, each [B, S*T, D] (rows (b,n,t)), filled in order
+ *   attentions    NULL or L device pointers, each fp32 [B*T, heads, S, S] (spatial probabilities) */
+int sf_forward(sf_ctx* ctx, void* stream, const void* pixels, int pixels_dtype, int B, int T, int H,
+               int W, void* last_hidden, void* pooler, void* const* hidden_states,
+               void* const* attentions, void* workspace, size_t workspace_bytes);
+
+/* ---- streaming (temporal KV cache) ------------------------------------------------------- */
+/* replaces transformers.DynamicCache as used by the KV twin (…timesformer_encoder.py:517-518,
+ * 1340-1349): pre-allocated [layer][K|V][B*S sites][heads][max_frames][64], appended in place.
+ * time_horizon: 0 = reference rule (time table stretched over frames seen so far when that exceeds
+ * num_frames, …timesformer_encoder.py:336-366); >0 = fixed horizon, making streaming identical to
+ * a one-shot forward of `time_horizon` frames. */
+int sf_kv_create(sf_ctx* ctx, int B, int S, int max_frames, int time_horizon, sf_kv** out);
+int sf_kv_reset(sf_kv* kv);
+int sf_kv_destroy(sf_kv* kv);
+int sf_kv_seq_len(const sf_kv* kv);
+int sf_kv_capacity(const sf_kv* kv);
+/* forward of T_new frames that attend to every cached frame (+ causal order among the new ones);
+ * outputs as sf_forward with T = T_new. Advances the cache by T_new. */
+int sf_forward_stream(sf_ctx* ctx, void* stream, sf_kv* kv, const void* pixels, int pixels_dtype,
+                      int B, int T_new, int H, int W, void* last_hidden, void* pooler,
+                      void* const* hidden_states, void* workspace, size_t workspace_bytes);
+
+/* ---- block-level API (what downstream/AR and the OVIS ViT-adapter call) ------------------- */
+/* TimesformerEmbeddingsSigLIP.forward (…siglip.py:413-457): pixels -> x [B, S*T, D] */
+int sf_embed_forward(sf_ctx* ctx, void* stream, const void* pixels, int pixels_dtype, int B, int T,
+                     int H, int W, int time_off, int time_total, void* x_out, void* workspace,
+                     size_t workspace_bytes);
+/* TimesformerLayerSigLIP.forward (…siglip.py:900-1004): x_in/x_out [B, S*T, D]; x_out may alias
+ * x_in; kv may be NULL; attn_probs NULL or fp32 [B*T, heads, S, S] */
+int sf_layer_forward(sf_ctx* ctx, void* stream, int layer, const void* x_in, void* x_out, int B,
+                     int T, int S, sf_kv* kv, float* attn_probs, void* workspace,
+                     size_t workspace_bytes);
+/* post_layernorm + (b,n,t)->(b,t,n) (…siglip.py:1330-1346): x [B, S*T, D] -> [B, T, S, D] */
+int sf_final_norm(sf_ctx* ctx, void* stream, const void* x, int B, int T, int S, void* last_hidden);
+/* TimesformerSiglipMultiheadAttentionPoolingHead.forward (…siglip.py:1141-1154):
+ * tokens [frames, S, D] -> pooled [frames, D] */
+int sf_head_forward(sf_ctx* ctx, void* stream, const void* tokens, int frames, int S, void* pooled,
+                    void* workspace, size_t workspace_bytes);
+
+/* ---- single kernels (parity tests, profiling) -------------------------------------------- */
+typedef struct sf_gemm_epilogue {
+  const float* bias; int act;
+  const void* residual; int ldr; const float* gate;
+  int row_map; int T; int S;
+  const float* pos; const float* time_emb; int time_len; int time_total; int time_off;
+} sf_gemm_epilogue;
+int sf_op_gemm(void* stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out,
+               int ldo, int M, int N, int K, const sf_gemm_epilogue* epi);
+int sf_op_layernorm(void* stream, int dtype, const void* x, int ldx, const float* gamma,
+                    const float* beta, float eps, void* y, int ldy, int M, int D, int row_map, int T,
+                    int S);
+int sf_op_im2col(void* stream, int pix_dtype, const void* pixels, int act_dtype, void* out, int BT,
+                 int C, int H, int W, int P);
+int sf_op_temporal_attention(void* stream, int dtype, const void* qkv, int ld_qkv, const void* kcache,
+                             const void* vcache, int Tcap, void* out, int ld_out, int sites, int heads,
+                             int Tq, int Tk, int q_off, int causal, float scale);
+int sf_op_kv_append(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
+                    int Tcap, int sites, int heads, int Tq, int pos0);
+int sf_op_spatial_attention(void* stream, int dtype, const void* qkv, int ld_qkv, void* out, int ld_out,
+                            int frames, int heads, int S, float scale, float* probs);
+int sf_op_pool_attention(void* stream, int dtype, const void* kv, int ld_kv, const float* q, void* out,
+                         int ld_out, int frames, int heads, int S);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMFORMER_B200_H_ */

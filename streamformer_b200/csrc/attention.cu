@@ -1,0 +1,527 @@
+// attention.cu — the attention cores of the encoder (head_dim = 64, fp32 softmax, flash-style
+// online normalisation, bf16/fp16 operands on the warp-level tensor-core path):
+//   * temporal attention over frames, causal (reference TimesformerCausalSelfAttention.forward,
+//     models/modeling_timesformer_siglip.py:575-615; KV-cache twin
+//     downstream/VideoQA/llava/model/multimodal_encoder/timesformer_encoder.py:491-560) or
+//     bidirectional (TimesformerSelfAttention, :688-717, when enable_causal_temporal=False);
+//     K/V come either from the fresh QKV projection or from the pre-allocated streaming cache.
+//   * spatial attention inside each frame (reference :688-717, lora_forward :649-683).
+//   * the probe-query pooling attention of the SigLIP head (reference :1141-1148).
+// These contractions are 3 % of the encoder FLOPs and HBM/L2-bound stand-alone, so they read
+// Q/K/V in place (128-byte head rows, no permute copies) and never materialise the score tensor.
+#include <math.h>
+
+#include <type_traits>
+
+#include "sf_kernels.h"
+#include "sf_ptx.cuh"
+
+namespace sf {
+namespace {
+
+constexpr int kHd = 64;                       // head dim
+constexpr float kLog2e = 1.4426950408889634f;
+
+// swizzled byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][64] 2-byte tile
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+  return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// Q fragments (A operand, 16 rows x 64) straight from global memory. Row g -> a[ks][0], a[ks][2];
+// row g+8 -> a[ks][1], a[ks][3].
+template <typename T>
+__device__ __forceinline__ void load_q_frags(uint32_t (&a)[4][4], const T* q0, const T* q1, bool ok0,
+                                             bool ok1, int c) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    a[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 2 * c) : 0u;
+    a[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 2 * c) : 0u;
+    a[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8 + 2 * c) : 0u;
+    a[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8 + 2 * c) : 0u;
+  }
+}
+
+// S(16 x 16 keys) = Q . K^T for the 16 keys starting at smem row `krow0` of the K tile.
+template <bool kBf16>
+__device__ __forceinline__ void qk_16keys(float (&s0)[4], float (&s1)[4], const uint32_t (&a)[4][4],
+                                          uint32_t k_smem, int krow0, int lane) {
+  const int mi = lane >> 3, rin = lane & 7;
+  const int row = krow0 + (mi >> 1) * 8 + rin;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t b[4];
+    ldmatrix_x4(b, k_smem + tile_off(row, 2 * ks + (mi & 1)));
+    mma_16816<kBf16>(s0, a[ks], b[0], b[1]);
+    mma_16816<kBf16>(s1, a[ks], b[2], b[3]);
+  }
+}
+
+// O(16 x 64) += P(16 x 16 keys) . V for the 16 keys starting at smem row `vrow0` of the V tile.
+template <bool kBf16>
+__device__ __forceinline__ void pv_16keys(float (&o)[8][4], const uint32_t (&pa)[4], uint32_t v_smem,
+                                          int vrow0, int lane) {
+  const int mi = lane >> 3, rin = lane & 7;
+  const int row = vrow0 + (mi & 1) * 8 + rin;
+#pragma unroll
+  for (int dp = 0; dp < 4; ++dp) {
+    uint32_t b[4];
+    ldmatrix_x4_trans(b, v_smem + tile_off(row, 2 * dp + (mi >> 1)));
+    mma_16816<kBf16>(o[2 * dp], pa, b[0], b[1]);
+    mma_16816<kBf16>(o[2 * dp + 1], pa, b[2], b[3]);
+  }
+}
+
+// One online-softmax step over a 16-key slab (two n-tiles s0, s1 already scaled+masked, log2 domain).
+// Produces the packed P fragments and rescales the running state.
+template <typename T>
+__device__ __forceinline__ void softmax_step(float (&s0)[4], float (&s1)[4], float (&m_run)[2],
+                                             float (&l_run)[2], float (&o)[8][4], uint32_t (&pa)[4]) {
+  float mx0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
+  float mx1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float mn0 = fmaxf(m_run[0], mx0), mn1 = fmaxf(m_run[1], mx1);
+  const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0;  // fully masked so far: avoid (-inf)-(-inf)
+  const float mu1 = (mn1 == -INFINITY) ? 0.f : mn1;
+  const float al0 = exp2f(m_run[0] - mu0), al1 = exp2f(m_run[1] - mu1);
+  m_run[0] = mn0;
+  m_run[1] = mn1;
+  const float p00 = exp2f(s0[0] - mu0), p01 = exp2f(s0[1] - mu0);
+  const float p02 = exp2f(s0[2] - mu1), p03 = exp2f(s0[3] - mu1);
+  const float p10 = exp2f(s1[0] - mu0), p11 = exp2f(s1[1] - mu0);
+  const float p12 = exp2f(s1[2] - mu1), p13 = exp2f(s1[3] - mu1);
+  l_run[0] = l_run[0] * al0 + (p00 + p01 + p10 + p11);
+  l_run[1] = l_run[1] * al1 + (p02 + p03 + p12 + p13);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    o[d][0] *= al0; o[d][1] *= al0; o[d][2] *= al1; o[d][3] *= al1;
+  }
+  pa[0] = Pack2<T>::pack(p00, p01);  // row g,   keys 2c..2c+1
+  pa[1] = Pack2<T>::pack(p02, p03);  // row g+8, keys 2c..
+  pa[2] = Pack2<T>::pack(p10, p11);  // row g,   keys 8+2c..
+  pa[3] = Pack2<T>::pack(p12, p13);  // row g+8, keys 8+2c..
+}
+
+template <typename T>
+__device__ __forceinline__ void finalize_store(float (&o)[8][4], float (&l_run)[2], T* out0, T* out1,
+                                               bool ok0, bool ok1, int c) {
+  float l0 = l_run[0], l1 = l_run[1];
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    if (ok0) *reinterpret_cast<uint32_t*>(out0 + d * 8 + 2 * c) = Pack2<T>::pack(o[d][0] * i0, o[d][1] * i0);
+    if (ok1) *reinterpret_cast<uint32_t*>(out1 + d * 8 + 2 * c) = Pack2<T>::pack(o[d][2] * i1, o[d][3] * i1);
+  }
+}
+
+// ------------------------------------------------------------------------------- temporal
+struct TemporalArgs {
+  const void* q;  long q_ld;                         // q row (site*Tq+i) at q + row*q_ld + h*64
+  const void* k;  const void* v;
+  long kv_site_stride, kv_head_stride, kv_row_stride;  // elements
+  void* out; long out_ld;
+  int sites, heads, Tq, Tk, q_off, causal, qtiles;
+  long tasks;
+  float scale_log2;
+};
+
+constexpr int kTWarps = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const TemporalArgs a) {
+  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+  __shared__ __align__(128) uint8_t smem[kTWarps][2][16 * 128];  // per warp: K tile, V tile
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const long task = static_cast<long>(blockIdx.x) * kTWarps + warp;
+  if (task >= a.tasks) return;
+  // task order: head fastest, then q-tile, then site
+  const int h = static_cast<int>(task % a.heads);
+  const long rest = task / a.heads;
+  const int qt = static_cast<int>(rest % a.qtiles);
+  const long site = rest / a.qtiles;
+  const int i0 = qt * 16;
+
+  const T* qbase = reinterpret_cast<const T*>(a.q) + (site * a.Tq) * a.q_ld + h * kHd;
+  const bool ok0 = (i0 + g) < a.Tq, ok1 = (i0 + g + 8) < a.Tq;
+  uint32_t qa[4][4];
+  load_q_frags<T>(qa, qbase + static_cast<long>(i0 + g) * a.q_ld, qbase + static_cast<long>(i0 + g + 8) * a.q_ld,
+                  ok0, ok1, c);
+
+  const T* kbase = reinterpret_cast<const T*>(a.k) + site * a.kv_site_stride + h * a.kv_head_stride;
+  const T* vbase = reinterpret_cast<const T*>(a.v) + site * a.kv_site_stride + h * a.kv_head_stride;
+  uint8_t* ks = smem[warp][0];
+  uint8_t* vs = smem[warp][1];
+  const uint32_t ks_u = smem_u32(ks), vs_u = smem_u32(vs);
+
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[8][4];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
+
+  int last_q = i0 + 15;
+  if (last_q > a.Tq - 1) last_q = a.Tq - 1;
+  int kmax = a.causal ? (a.q_off + last_q + 1) : a.Tk;
+  if (kmax > a.Tk) kmax = a.Tk;
+
+  for (int kb0 = 0; kb0 < kmax; kb0 += 16) {
+    // stage K/V rows kb0..kb0+15 (zero-filled past Tk)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = lane + 32 * i;
+      const int row = idx >> 3, ch = idx & 7;
+      const bool ok = (kb0 + row) < a.Tk;
+      const long roff = static_cast<long>(ok ? kb0 + row : 0) * a.kv_row_stride + ch * 8;
+      cp_async_16(ks + tile_off(row, ch), kbase + roff, ok);
+      cp_async_16(vs + tile_off(row, ch), vbase + roff, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    qk_16keys<kBf16>(s0, s1, qa, ks_u, 0, lane);
+    // scale (log2 domain) + mask
+    const int lim0 = a.causal ? (a.q_off + i0 + g) : (a.Tk - 1);
+    const int lim1 = a.causal ? (a.q_off + i0 + g + 8) : (a.Tk - 1);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j0 = kb0 + 2 * c + e, j1 = kb0 + 8 + 2 * c + e;
+      s0[e] = (j0 < a.Tk && j0 <= lim0) ? s0[e] * a.scale_log2 : -INFINITY;
+      s0[2 + e] = (j0 < a.Tk && j0 <= lim1) ? s0[2 + e] * a.scale_log2 : -INFINITY;
+      s1[e] = (j1 < a.Tk && j1 <= lim0) ? s1[e] * a.scale_log2 : -INFINITY;
+      s1[2 + e] = (j1 < a.Tk && j1 <= lim1) ? s1[2 + e] * a.scale_log2 : -INFINITY;
+    }
+    uint32_t pa[4];
+    softmax_step<T>(s0, s1, m_run, l_run, o, pa);
+    pv_16keys<kBf16>(o, pa, vs_u, 0, lane);
+    __syncwarp();  // tile is reused by the next slab
+  }
+
+  T* obase = reinterpret_cast<T*>(a.out) + (site * a.Tq) * a.out_ld + h * kHd;
+  finalize_store<T>(o, l_run, obase + static_cast<long>(i0 + g) * a.out_ld,
+                    obase + static_cast<long>(i0 + g + 8) * a.out_ld, ok0, ok1, c);
+}
+
+// K/V slices of the fresh QKV projection -> cache[site][head][pos0 + i][64]
+template <typename T>
+__global__ void __launch_bounds__(256)
+kv_append_kernel(const T* __restrict__ qkv, long ld, T* __restrict__ kc, T* __restrict__ vc, int Tcap,
+                 int sites, int heads, int Tq, int pos0) {
+  const int D = heads * kHd;
+  const long total = static_cast<long>(sites) * Tq * heads * 8;  // 16-byte chunks per K (and per V)
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i & 7);
+    long r = i >> 3;
+    const int h = static_cast<int>(r % heads);
+    r /= heads;
+    const int t = static_cast<int>(r % Tq);
+    const long site = r / Tq;
+    const T* src = qkv + (site * Tq + t) * ld + D + h * kHd + ch * 8;
+    const long dst = ((site * heads + h) * Tcap + pos0 + t) * kHd + ch * 8;
+    *reinterpret_cast<uint4*>(kc + dst) = *reinterpret_cast<const uint4*>(src);
+    *reinterpret_cast<uint4*>(vc + dst) = *reinterpret_cast<const uint4*>(src + D);
+  }
+}
+
+// ------------------------------------------------------------------------------- spatial
+constexpr int kSWarps = 4;        // 64 query rows per CTA
+constexpr int kSKeys = 64;        // keys per pipeline stage
+
+struct SpatialArgs {
+  const void* qkv; long ld;
+  void* out; long out_ld;
+  int frames, heads, S, qblocks;
+  float scale_log2;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kSWarps * 32) spatial_attn_kernel(const SpatialArgs a) {
+  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+  __shared__ __align__(128) uint8_t smem[2][2][kSKeys * 128];  // [stage][K|V]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int D = a.heads * kHd;
+  int bid = blockIdx.x;
+  const int qb = bid % a.qblocks;
+  bid /= a.qblocks;
+  const int h = bid % a.heads;
+  const long frame = bid / a.heads;
+
+  const T* base = reinterpret_cast<const T*>(a.qkv) + frame * a.S * a.ld + h * kHd;
+  const T* kbase = base + D;
+  const T* vbase = base + 2 * D;
+  const int i0 = qb * (kSWarps * 16) + warp * 16;
+  const bool warp_active = i0 < a.S;
+  const bool ok0 = (i0 + g) < a.S, ok1 = (i0 + g + 8) < a.S;
+
+  uint32_t qa[4][4];
+  load_q_frags<T>(qa, base + static_cast<long>(i0 + g) * a.ld, base + static_cast<long>(i0 + g + 8) * a.ld,
+                  ok0, ok1, c);
+
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[8][4];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
+
+  const int nblocks = (a.S + kSKeys - 1) / kSKeys;
+  auto prefetch = [&](int kb, int stage) {
+    const int kb0 = kb * kSKeys;
+#pragma unroll
+    for (int i = 0; i < (kSKeys * 8) / (kSWarps * 32); ++i) {
+      const int idx = threadIdx.x + i * (kSWarps * 32);
+      const int row = idx >> 3, ch = idx & 7;
+      const bool ok = (kb0 + row) < a.S;
+      const long roff = static_cast<long>(ok ? kb0 + row : 0) * a.ld + ch * 8;
+      cp_async_16(smem[stage][0] + tile_off(row, ch), kbase + roff, ok);
+      cp_async_16(smem[stage][1] + tile_off(row, ch), vbase + roff, ok);
+    }
+    cp_async_commit();
+  };
+
+  prefetch(0, 0);
+  for (int kb = 0; kb < nblocks; ++kb) {
+    const int stage = kb & 1;
+    if (kb + 1 < nblocks) {
+      prefetch(kb + 1, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (warp_active) {
+      const int kb0 = kb * kSKeys;
+      int nsub = (a.S - kb0 + 15) >> 4;   // valid 16-key slabs in this block
+      if (nsub > kSKeys / 16) nsub = kSKeys / 16;
+      const uint32_t ks_u = smem_u32(smem[stage][0]), vs_u = smem_u32(smem[stage][1]);
+#pragma unroll
+      for (int sub = 0; sub < kSKeys / 16; ++sub) {
+        if (sub < nsub) {
+          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+          qk_16keys<kBf16>(s0, s1, qa, ks_u, sub * 16, lane);
+          const int kk = kb0 + sub * 16;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool v0 = (kk + 2 * c + e) < a.S, v1 = (kk + 8 + 2 * c + e) < a.S;
+            s0[e] = v0 ? s0[e] * a.scale_log2 : -INFINITY;
+            s0[2 + e] = v0 ? s0[2 + e] * a.scale_log2 : -INFINITY;
+            s1[e] = v1 ? s1[e] * a.scale_log2 : -INFINITY;
+            s1[2 + e] = v1 ? s1[2 + e] * a.scale_log2 : -INFINITY;
+          }
+          uint32_t pa[4];
+          softmax_step<T>(s0, s1, m_run, l_run, o, pa);
+          pv_16keys<kBf16>(o, pa, vs_u, sub * 16, lane);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (warp_active) {
+    T* obase = reinterpret_cast<T*>(a.out) + frame * a.S * a.out_ld + h * kHd;
+    finalize_store<T>(o, l_run, obase + static_cast<long>(i0 + g) * a.out_ld,
+                      obase + static_cast<long>(i0 + g + 8) * a.out_ld, ok0, ok1, c);
+  }
+}
+
+// Debug path (output_attentions=True): normalised probabilities, one warp per query row.
+template <typename T>
+__global__ void __launch_bounds__(128)
+spatial_probs_kernel(const T* __restrict__ qkv, long ld, float* __restrict__ probs, int frames, int heads,
+                     int S, float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row_id = static_cast<long>(blockIdx.x) * 4 + warp;  // (frame, head, query)
+  const long total = static_cast<long>(frames) * heads * S;
+  if (row_id >= total) return;
+  const int qi = static_cast<int>(row_id % S);
+  const int h = static_cast<int>((row_id / S) % heads);
+  const long frame = row_id / (static_cast<long>(S) * heads);
+  const int D = heads * kHd;
+  const T* base = qkv + frame * S * ld + h * kHd;
+  const T* q = base + static_cast<long>(qi) * ld;
+  float* prow = probs + row_id * S;
+  float qf[2];
+  {
+    const float2 t = Pack2<T>::unpack(*reinterpret_cast<const uint32_t*>(q + 2 * lane));
+    qf[0] = t.x; qf[1] = t.y;
+  }
+  float mx = -INFINITY;
+  for (int j = 0; j < S; ++j) {
+    const float2 kf = Pack2<T>::unpack(*reinterpret_cast<const uint32_t*>(base + D + static_cast<long>(j) * ld + 2 * lane));
+    const float s = warp_sum(qf[0] * kf.x + qf[1] * kf.y) * scale;
+    if (lane == 0) prow[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < S; j += 32) {
+    const float e = __expf(prow[j] - mx);
+    prow[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < S; j += 32) prow[j] *= inv;
+}
+
+// ------------------------------------------------------------------------------- pooling probe
+// one warp per (frame, head): scores over S keys against a fixed fp32 query, softmax, weighted V sum
+constexpr int kPoolMaxS = 1024;
+template <typename T>
+__global__ void __launch_bounds__(128)
+pool_attn_kernel(const T* __restrict__ kv, long ld, const float* __restrict__ q, T* __restrict__ out,
+                 long out_ld, int frames, int heads, int S) {
+  __shared__ float sc[4][kPoolMaxS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long task = static_cast<long>(blockIdx.x) * 4 + warp;
+  if (task >= static_cast<long>(frames) * heads) return;
+  const int h = static_cast<int>(task % heads);
+  const long frame = task / heads;
+  const int D = heads * kHd;
+  const T* kb = kv + frame * S * ld + h * kHd;
+  const T* vb = kb + D;
+  const float* qh = q + h * kHd;
+  float mx = -INFINITY;
+  for (int n = lane; n < S; n += 32) {
+    const T* kr = kb + static_cast<long>(n) * ld;
+    float acc = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const uint4 u = *reinterpret_cast<const uint4*>(kr + ch * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = Pack2<T>::unpack(w[j]);
+        acc += f.x * __ldg(qh + ch * 8 + 2 * j) + f.y * __ldg(qh + ch * 8 + 2 * j + 1);
+      }
+    }
+    sc[warp][n] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int n = lane; n < S; n += 32) {
+    const float e = __expf(sc[warp][n] - mx);
+    sc[warp][n] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  float o0 = 0.f, o1 = 0.f;  // lane owns dims 2*lane, 2*lane+1
+  for (int n = 0; n < S; ++n) {
+    const float p = sc[warp][n];
+    const float2 f = Pack2<T>::unpack(*reinterpret_cast<const uint32_t*>(vb + static_cast<long>(n) * ld + 2 * lane));
+    o0 += p * f.x;
+    o1 += p * f.y;
+  }
+  *reinterpret_cast<uint32_t*>(out + frame * out_ld + h * kHd + 2 * lane) = Pack2<T>::pack(o0 * inv, o1 * inv);
+}
+
+int check_launch(const char* what) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, const void* kcache,
+                       const void* vcache, int Tcap, void* out, int ld_out, int sites, int heads, int Tq,
+                       int Tk, int q_off, int causal, float scale) {
+  if (sites <= 0 || Tq <= 0) return 0;
+  if (dtype != kBF16 && dtype != kF16) { set_error("temporal_attention: dtype must be bf16/f16"); return -1; }
+  if ((ld_qkv % 8) || (ld_out % 2)) { set_error("temporal_attention: bad leading dims"); return -1; }
+  const int D = heads * kHd;
+  TemporalArgs a;
+  a.q = qkv; a.q_ld = ld_qkv;
+  const size_t es = 2;
+  if (kcache) {
+    if (Tk > Tcap) { set_error("temporal_attention: Tk=%d exceeds cache capacity %d", Tk, Tcap); return -1; }
+    a.k = kcache; a.v = vcache;
+    a.kv_site_stride = static_cast<long>(heads) * Tcap * kHd;
+    a.kv_head_stride = static_cast<long>(Tcap) * kHd;
+    a.kv_row_stride = kHd;
+  } else {
+    if (Tk != Tq) { set_error("temporal_attention: Tk must equal Tq without a cache"); return -1; }
+    a.k = reinterpret_cast<const uint8_t*>(qkv) + static_cast<size_t>(D) * es;
+    a.v = reinterpret_cast<const uint8_t*>(qkv) + static_cast<size_t>(2 * D) * es;
+    a.kv_site_stride = static_cast<long>(Tq) * ld_qkv;
+    a.kv_head_stride = kHd;
+    a.kv_row_stride = ld_qkv;
+  }
+  a.out = out; a.out_ld = ld_out;
+  a.sites = sites; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.q_off = q_off; a.causal = causal;
+  a.qtiles = (Tq + 15) / 16;
+  a.tasks = static_cast<long>(sites) * heads * a.qtiles;
+  a.scale_log2 = scale * kLog2e;
+  const long blocks = (a.tasks + kTWarps - 1) / kTWarps;
+  if (dtype == kBF16) temporal_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kTWarps * 32, 0, stream>>>(a);
+  else temporal_attn_kernel<__half><<<static_cast<unsigned>(blocks), kTWarps * 32, 0, stream>>>(a);
+  return check_launch("temporal_attention");
+}
+
+int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
+              int Tcap, int sites, int heads, int Tq, int pos0) {
+  if (sites <= 0 || Tq <= 0) return 0;
+  if (pos0 + Tq > Tcap) { set_error("kv_append: %d + %d frames exceed cache capacity %d", pos0, Tq, Tcap); return -1; }
+  const long total = static_cast<long>(sites) * Tq * heads * 8;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  // bf16 and fp16 are both 2-byte payloads: one instantiation moves either
+  kv_append_kernel<__nv_bfloat16><<<static_cast<int>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv, reinterpret_cast<__nv_bfloat16*>(kcache),
+      reinterpret_cast<__nv_bfloat16*>(vcache), Tcap, sites, heads, Tq, pos0);
+  (void)dtype;
+  return check_launch("kv_append");
+}
+
+int spatial_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* out, int ld_out,
+                      int frames, int heads, int S, float scale, float* probs) {
+  if (frames <= 0 || S <= 0) return 0;
+  if (dtype != kBF16 && dtype != kF16) { set_error("spatial_attention: dtype must be bf16/f16"); return -1; }
+  if ((ld_qkv % 8) || (ld_out % 2)) { set_error("spatial_attention: bad leading dims"); return -1; }
+  SpatialArgs a;
+  a.qkv = qkv; a.ld = ld_qkv; a.out = out; a.out_ld = ld_out;
+  a.frames = frames; a.heads = heads; a.S = S;
+  a.qblocks = (S + kSWarps * 16 - 1) / (kSWarps * 16);
+  a.scale_log2 = scale * kLog2e;
+  const long blocks = static_cast<long>(frames) * heads * a.qblocks;
+  if (dtype == kBF16) spatial_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kSWarps * 32, 0, stream>>>(a);
+  else spatial_attn_kernel<__half><<<static_cast<unsigned>(blocks), kSWarps * 32, 0, stream>>>(a);
+  int rc = check_launch("spatial_attention");
+  if (rc || !probs) return rc;
+  const long rows = static_cast<long>(frames) * heads * S;
+  const long pb = (rows + 3) / 4;
+  if (dtype == kBF16) spatial_probs_kernel<__nv_bfloat16><<<static_cast<unsigned>(pb), 128, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv, probs, frames, heads, S, scale);
+  else spatial_probs_kernel<__half><<<static_cast<unsigned>(pb), 128, 0, stream>>>(
+      reinterpret_cast<const __half*>(qkv), ld_qkv, probs, frames, heads, S, scale);
+  return check_launch("spatial_probs");
+}
+
+int pool_attention(cudaStream_t stream, int dtype, const void* kv, int ld_kv, const float* q, void* out,
+                   int ld_out, int frames, int heads, int S) {
+  if (frames <= 0) return 0;
+  if (S > kPoolMaxS) { set_error("pool_attention: S=%d exceeds %d", S, kPoolMaxS); return -1; }
+  if (dtype != kBF16 && dtype != kF16) { set_error("pool_attention: dtype must be bf16/f16"); return -1; }
+  const long tasks = static_cast<long>(frames) * heads;
+  const long blocks = (tasks + 3) / 4;
+  if (dtype == kBF16) pool_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(kv), ld_kv, q, reinterpret_cast<__nv_bfloat16*>(out), ld_out, frames, heads, S);
+  else pool_attn_kernel<__half><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
+      reinterpret_cast<const __half*>(kv), ld_kv, q, reinterpret_cast<__half*>(out), ld_out, frames, heads, S);
+  return check_launch("pool_attention");
+}
+
+}  // namespace sf

@@ -1,0 +1,84 @@
+// common.cu — error string, launch counter and small element-wise helpers shared by the library.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "sf_kernels.h"
+#include "sf_ptx.cuh"
+
+namespace sf {
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+const char* last_error() { return g_err; }
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+uint64_t launch_count() { return g_launches.load(); }
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }
+
+namespace {
+
+template <typename S>
+__device__ __forceinline__ float to_f32(S v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename D>
+__device__ __forceinline__ D from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) dst[i] = from_f32<D>(to_f32<S>(src[i]));
+}
+
+template <typename S>
+int cast_dispatch_dst(cudaStream_t st, const void* src, int dd, void* dst, size_t n) {
+  const int threads = 256;
+  size_t want = (n + threads - 1) / threads;
+  int blocks = static_cast<int>(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+  const S* s = reinterpret_cast<const S*>(src);
+  switch (dd) {
+    case kBF16: cast_kernel<S, __nv_bfloat16><<<blocks, threads, 0, st>>>(s, reinterpret_cast<__nv_bfloat16*>(dst), n); break;
+    case kF16: cast_kernel<S, __half><<<blocks, threads, 0, st>>>(s, reinterpret_cast<__half*>(dst), n); break;
+    case kF32: cast_kernel<S, float><<<blocks, threads, 0, st>>>(s, reinterpret_cast<float*>(dst), n); break;
+    default: set_error("cast: bad dst dtype %d", dd); return -1;
+  }
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("cast launch: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+}  // namespace
+
+int cast(cudaStream_t stream, int sd, const void* src, int dd, void* dst, size_t n) {
+  if (n == 0) return 0;
+  switch (sd) {
+    case kBF16: return cast_dispatch_dst<__nv_bfloat16>(stream, src, dd, dst, n);
+    case kF16: return cast_dispatch_dst<__half>(stream, src, dd, dst, n);
+    case kF32: return cast_dispatch_dst<float>(stream, src, dd, dst, n);
+    default: set_error("cast: bad src dtype %d", sd); return -1;
+  }
+}
+
+}  // namespace sf

@@ -1,0 +1,407 @@
+// gemm_tcgen05.cu — the workhorse of the StreamFormer encoder: every projection on the hot path
+// (patch-embed conv-as-GEMM, temporal/spatial QKV, attention out-proj, temporal_dense, MLP fc1/fc2,
+// pooling-head K/V/out/MLP; reference nn.Linear / nn.Conv2d call sites:
+// models/modeling_timesformer_siglip.py:329-350, 513, 578, 629, 691, 728, 760, 811, 820, 830, 834,
+// 895, 954, 1118-1124, 1135) runs through this one persistent, warp-specialised kernel:
+//
+//   warp 0        TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 4-stage ring)
+//   warp 1        MMA issuer     (tcgen05.mma kind::f16, 128 x BN x 16 per instruction, fp32 in TMEM)
+//   warps 2..9    epilogue       (tcgen05.ld -> bias / GELU / pos+time embed / gated residual ->
+//                                 16-byte global stores, optional (b,t,n)<->(b,n,t) row permutation)
+//
+// TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <math.h>
+
+#include "sf_kernels.h"
+#include "sf_ptx.cuh"
+
+namespace sf {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;             // 64 x 2 B = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
+
+struct GemmParams {
+  int M, N, K;
+  void* out;
+  int ldo;
+  GemmEpilogue epi;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <typename T> struct UmmaFmt;
+template <> struct UmmaFmt<__half> { static constexpr int value = 0; };
+template <> struct UmmaFmt<__nv_bfloat16> { static constexpr int value = 1; };
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+
+// nearest-neighbour source index, identical arithmetic to F.interpolate(mode="nearest"):
+// scale = float(in)/out ; src = min(floor(dst*scale), in-1)
+__device__ __forceinline__ int time_index(int t_abs, int time_len, int time_total) {
+  if (time_total <= time_len) return t_abs;
+  float scale = static_cast<float>(time_len) / static_cast<float>(time_total);
+  int s = static_cast<int>(floorf(static_cast<float>(t_abs) * scale));
+  return s < time_len - 1 ? s : time_len - 1;
+}
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN, UmmaFmt<T>::value);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t da = umma_desc_sw128_kmajor(sa);
+          const uint64_t db = umma_desc_sw128_kmajor(sb);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
+            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;              // which half of the BN columns
+    constexpr int kColsPerWarp = BN / 2;
+    const GemmEpilogue& e = p.epi;
+    const float gscale = e.gate ? tanhf(__ldg(e.gate)) : 1.0f;
+    T* out = reinterpret_cast<T*>(p.out);
+    const T* res = reinterpret_cast<const T*>(e.residual);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * kBM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      // row decomposition / permutation
+      long r = m;
+      int site = 0, frame = 0;
+      if (e.row_map == kRowBTNtoBNT || e.pos != nullptr || e.time_emb != nullptr) {
+        // m = (b*T + t)*S + n
+        site = m % e.S;
+        const int bt = m / e.S;
+        frame = bt % e.T;
+        const int b = bt / e.T;
+        if (e.row_map == kRowBTNtoBNT) r = (static_cast<long>(b) * e.S + site) * e.T + frame;
+      } else if (e.row_map == kRowBNTtoBTN) {
+        // m = (b*S + n)*T + t
+        frame = m % e.T;
+        const int bn = m / e.T;
+        site = bn % e.S;
+        const int b = bn / e.S;
+        r = (static_cast<long>(b) * e.T + frame) * e.S + site;
+      }
+      const float* pos_row = e.pos ? e.pos + static_cast<long>(site) * p.N : nullptr;
+      const float* time_row =
+          e.time_emb ? e.time_emb + static_cast<long>(time_index(e.time_off + frame, e.time_len,
+                                                                e.time_total)) * p.N
+                     : nullptr;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
+                              half * kColsPerWarp;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(t_base + c * 32, raw);
+        tmem_ld_wait();
+        const int col0 = n0 + half * kColsPerWarp + c * 32;
+        if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns = one 16-byte store each
+            const int col = col0 + g * 8;
+            if (col < p.N) {
+              float* vv = v + g * 8;
+              if (e.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
+                vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+                vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+              }
+              if (e.act == kActGeluErf) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
+              } else if (e.act == kActGeluTanh) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
+              }
+              if (pos_row) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + col + 4));
+                vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+                vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+              }
+              if (time_row) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(time_row + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(time_row + col + 4));
+                vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+                vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+              }
+              if (res) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(res + r * e.ldr + col);
+                const float2 r0 = Pack2<T>::unpack(rr.x), r1 = Pack2<T>::unpack(rr.y);
+                const float2 r2 = Pack2<T>::unpack(rr.z), r3 = Pack2<T>::unpack(rr.w);
+                vv[0] = r0.x + gscale * vv[0]; vv[1] = r0.y + gscale * vv[1];
+                vv[2] = r1.x + gscale * vv[2]; vv[3] = r1.y + gscale * vv[3];
+                vv[4] = r2.x + gscale * vv[4]; vv[5] = r2.y + gscale * vv[5];
+                vv[6] = r3.x + gscale * vv[6]; vv[7] = r3.y + gscale * vv[7];
+              } else if (e.gate) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] *= gscale;
+              }
+              uint4 o;
+              o.x = Pack2<T>::pack(vv[0], vv[1]);
+              o.y = Pack2<T>::pack(vv[2], vv[3]);
+              o.z = Pack2<T>::pack(vv[4], vv[5]);
+              o.w = Pack2<T>::pack(vv[6], vv[7]);
+              *reinterpret_cast<uint4*>(out + r * p.ldo + col) = o;
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(err));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// 2D K-major operand map: dims {K, rows}, box {64, box_rows}, 128B swizzle, zero OOB fill.
+int make_operand_map(CUtensorMap* map, int dtype, const void* base, int rows, int K, int ld,
+                     int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -3;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt =
+      dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rows=%d K=%d ld=%d base=%p", (int)r, rows, K, ld,
+              base);
+    return -3;
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename T, int BN>
+int launch_gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw,
+                const GemmParams& p) {
+  using L = SmemLayout<BN>;
+  CUtensorMap tmA, tmB;
+  int rc = make_operand_map(&tmA, dtype, A, p.M, p.K, lda, kBM);
+  if (rc) return rc;
+  rc = make_operand_map(&tmB, dtype, W, p.N, p.K, ldw, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm smem=%d): %s", L::kTotal, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tcgen05_kernel<T, BN><<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, p);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("gemm launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out,
+         int ldo, int M, int N, int K, const GemmEpilogue& epi) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((K % 8) || (N % 8) || (lda % 8) || (ldw % 8) || (ldo % 8) || (epi.residual && (epi.ldr % 8))) {
+    set_error("gemm: K, N and leading dims must be multiples of 8 (M=%d N=%d K=%d lda=%d ldw=%d ldo=%d)",
+              M, N, K, lda, ldw, ldo);
+    return -1;
+  }
+  if (dtype != kBF16 && dtype != kF16) {
+    set_error("gemm: dtype must be bf16 or f16");
+    return -1;
+  }
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.epi = epi;
+  // 128x256 tiles when they fill the machine, 128x128 for small problems (more CTAs in flight).
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const bool wide = (N >= 256) && (m_tiles * ((N + 255) / 256) >= num_sms());
+  if (dtype == kBF16) {
+    return wide ? launch_gemm<__nv_bfloat16, 256>(stream, dtype, A, lda, W, ldw, p)
+                : launch_gemm<__nv_bfloat16, 128>(stream, dtype, A, lda, W, ldw, p);
+  }
+  return wide ? launch_gemm<__half, 256>(stream, dtype, A, lda, W, ldw, p)
+              : launch_gemm<__half, 128>(stream, dtype, A, lda, W, ldw, p);
+}
+
+}  // namespace sf

@@ -1,0 +1,237 @@
+// rowwise.cu — the HBM-bound row kernels of the encoder:
+//   * LayerNorm (reference: nn.LayerNorm at models/modeling_timesformer_siglip.py:860-880, 943, 974,
+//     997, 1251, 1330, 1138) — one warp per token row, fp32 statistics, 16-byte loads/stores,
+//     optional (b,n,t)<->(b,t,n) row permutation on the way out (replaces the reference's
+//     materialised permute copies at :962-971, 982-991, 1332-1346).
+//   * im2col for the 16x16/s16 patch-embedding conv (reference :336-350): pixels -> patch-major
+//     GEMM operand with K ordered (c, kh, kw), cast to the activation dtype on the fly.
+#include "sf_kernels.h"
+#include "sf_ptx.cuh"
+
+namespace sf {
+namespace {
+
+constexpr int kLnMaxChunks = 4;  // register-cached path covers D <= 8*32*4 = 1024
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, T* __restrict__ y, int ldy, int M, int D,
+                 int row_map, int Tn, int Sn) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nchunks = D >> 3;  // 8 elements (16 bytes) per chunk
+  for (long m = static_cast<long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); m < M;
+       m += static_cast<long>(gridDim.x) * warps_per_block) {
+    const T* xr = x + m * ldx;
+    float v[kLnMaxChunks][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxChunks; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
+        const float2 a = Pack2<T>::unpack(u.x), b = Pack2<T>::unpack(u.y);
+        const float2 cc = Pack2<T>::unpack(u.z), d = Pack2<T>::unpack(u.w);
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
+        v[i][4] = cc.x; v[i][5] = cc.y; v[i][6] = d.x; v[i][7] = d.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[i][j];
+      }
+    }
+    // chunks beyond the register cache (D > 1024): re-read
+    for (int c = lane + 32 * kLnMaxChunks; c < nchunks; c += 32) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
+      const float2 a = Pack2<T>::unpack(u.x), b = Pack2<T>::unpack(u.y);
+      const float2 cc = Pack2<T>::unpack(u.z), d = Pack2<T>::unpack(u.w);
+      sum += a.x + a.y + b.x + b.y + cc.x + cc.y + d.x + d.y;
+    }
+    const float mean = warp_sum(sum) / static_cast<float>(D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxChunks; ++i) {
+      if (lane + 32 * i < nchunks) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    for (int c = lane + 32 * kLnMaxChunks; c < nchunks; c += 32) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = Pack2<T>::unpack(w[j]);
+        sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
+
+    long r = m;
+    if (row_map == kRowBNTtoBTN) {
+      const long t = m % Tn, bn = m / Tn;
+      const long n = bn % Sn, b = bn / Sn;
+      r = (b * Tn + t) * Sn + n;
+    } else if (row_map == kRowBTNtoBNT) {
+      const long n = m % Sn, bt = m / Sn;
+      const long t = bt % Tn, b = bt / Tn;
+      r = (b * Sn + n) * Tn + t;
+    }
+    T* yr = y + r * ldy;
+    auto emit = [&](int c, const float (&vals)[8]) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c * 8 + 4));
+      uint4 o;
+      o.x = Pack2<T>::pack((vals[0] - mean) * rstd * g0.x + b0.x, (vals[1] - mean) * rstd * g0.y + b0.y);
+      o.y = Pack2<T>::pack((vals[2] - mean) * rstd * g0.z + b0.z, (vals[3] - mean) * rstd * g0.w + b0.w);
+      o.z = Pack2<T>::pack((vals[4] - mean) * rstd * g1.x + b1.x, (vals[5] - mean) * rstd * g1.y + b1.y);
+      o.w = Pack2<T>::pack((vals[6] - mean) * rstd * g1.z + b1.z, (vals[7] - mean) * rstd * g1.w + b1.w);
+      *reinterpret_cast<uint4*>(yr + c * 8) = o;
+    };
+#pragma unroll
+    for (int i = 0; i < kLnMaxChunks; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) emit(c, v[i]);
+    }
+    for (int c = lane + 32 * kLnMaxChunks; c < nchunks; c += 32) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
+      const float2 a = Pack2<T>::unpack(u.x), b = Pack2<T>::unpack(u.y);
+      const float2 cc = Pack2<T>::unpack(u.z), d = Pack2<T>::unpack(u.w);
+      const float vals[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+      emit(c, vals);
+    }
+  }
+}
+
+template <typename PixT>
+__device__ __forceinline__ void load8(const PixT* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = Pack2<__nv_bfloat16>::unpack(w[j]);
+    f[2 * j] = t.x; f[2 * j + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = Pack2<__half>::unpack(w[j]);
+    f[2 * j] = t.x; f[2 * j + 1] = t.y;
+  }
+}
+
+// one thread = 8 consecutive kw of one (patch row m, channel c, kernel row kh)
+template <typename PixT, typename T>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int BT, int C, int H, int W, int P) {
+  const int gw = W / P, gh = H / P;
+  const int S = gw * gh;
+  const int K = C * P * P;
+  const int chunks_per_row = K >> 3;
+  const long total = static_cast<long>(BT) * S * chunks_per_row;
+  const int pc = P >> 3;  // chunks per kernel row
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % chunks_per_row);
+    const long m = i / chunks_per_row;
+    const int n = static_cast<int>(m % S);
+    const long bt = m / S;
+    const int ph = n / gw, pw = n % gw;
+    const int part = j % pc;
+    const int kh = (j / pc) % P;
+    const int c = j / (pc * P);
+    const PixT* src = pix + ((bt * C + c) * H + (ph * P + kh)) * static_cast<long>(W) + pw * P + part * 8;
+    float f[8];
+    load8<PixT>(src, f);
+    uint4 o;
+    o.x = Pack2<T>::pack(f[0], f[1]);
+    o.y = Pack2<T>::pack(f[2], f[3]);
+    o.z = Pack2<T>::pack(f[4], f[5]);
+    o.w = Pack2<T>::pack(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + m * K + j * 8) = o;
+  }
+}
+
+template <typename PixT, typename T>
+int launch_im2col(cudaStream_t st, const void* pix, void* out, int BT, int C, int H, int W, int P) {
+  const long total = static_cast<long>(BT) * (H / P) * (W / P) * (C * P * P / 8);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 32) blocks = 148L * 32;
+  if (blocks < 1) blocks = 1;
+  im2col_kernel<PixT, T><<<static_cast<int>(blocks), 256, 0, st>>>(
+      reinterpret_cast<const PixT*>(pix), reinterpret_cast<T*>(out), BT, C, H, W, P);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("im2col launch: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+}  // namespace
+
+int layernorm(cudaStream_t stream, int dtype, const void* x, int ldx, const float* gamma,
+              const float* beta, float eps, void* y, int ldy, int M, int D, int row_map, int T, int S) {
+  if (M <= 0) return 0;
+  if ((D % 8) || (ldx % 8) || (ldy % 8)) {
+    set_error("layernorm: D, ldx, ldy must be multiples of 8 (D=%d ldx=%d ldy=%d)", D, ldx, ldy);
+    return -1;
+  }
+  const int threads = 256, wpb = threads / 32;
+  long blocks = (static_cast<long>(M) + wpb - 1) / wpb;
+  if (blocks > 148L * 8 * 4) blocks = 148L * 8 * 4;
+  if (dtype == kBF16) {
+    layernorm_kernel<__nv_bfloat16><<<static_cast<int>(blocks), threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps,
+        reinterpret_cast<__nv_bfloat16*>(y), ldy, M, D, row_map, T, S);
+  } else if (dtype == kF16) {
+    layernorm_kernel<__half><<<static_cast<int>(blocks), threads, 0, stream>>>(
+        reinterpret_cast<const __half*>(x), ldx, gamma, beta, eps, reinterpret_cast<__half*>(y), ldy,
+        M, D, row_map, T, S);
+  } else {
+    set_error("layernorm: dtype must be bf16 or f16");
+    return -1;
+  }
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("layernorm launch: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+int im2col_patches(cudaStream_t stream, int pix_dtype, const void* pixels, int act_dtype, void* out,
+                   int BT, int C, int H, int W, int P) {
+  if (BT <= 0) return 0;
+  if ((P % 8) || (H % P) || (W % P)) {
+    set_error("im2col: patch size must be a multiple of 8 and divide H, W (H=%d W=%d P=%d)", H, W, P);
+    return -1;
+  }
+#define SF_IM2COL(PT, AT) return launch_im2col<PT, AT>(stream, pixels, out, BT, C, H, W, P)
+  if (act_dtype == kBF16) {
+    if (pix_dtype == kF32) SF_IM2COL(float, __nv_bfloat16);
+    if (pix_dtype == kBF16) SF_IM2COL(__nv_bfloat16, __nv_bfloat16);
+    if (pix_dtype == kF16) SF_IM2COL(__half, __nv_bfloat16);
+  } else if (act_dtype == kF16) {
+    if (pix_dtype == kF32) SF_IM2COL(float, __half);
+    if (pix_dtype == kBF16) SF_IM2COL(__nv_bfloat16, __half);
+    if (pix_dtype == kF16) SF_IM2COL(__half, __half);
+  }
+#undef SF_IM2COL
+  set_error("im2col: unsupported dtypes pix=%d act=%d", pix_dtype, act_dtype);
+  return -1;
+}
+
+}  // namespace sf

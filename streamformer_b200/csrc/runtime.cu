@@ -1,0 +1,761 @@
+// runtime.cu — host-side schedule of the StreamFormer encoder behind the C ABI
+// (include/streamformer_b200.h): weight packing, workspace carving, the per-layer kernel sequence
+// of TimesformerLayerSigLIP.forward (models/modeling_timesformer_siglip.py:900-1004), the embedding
+// front end (:413-457), the final norm + pooling head (:1330-1346, 1141-1154) and the streaming
+// KV cache (downstream/VideoQA/llava/model/multimodal_encoder/timesformer_encoder.py:307-375,
+// 491-560, 1340-1349).
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/streamformer_b200.h"
+#include "sf_kernels.h"
+#include "sf_ptx.cuh"
+
+using namespace sf;
+
+#define SF_CHECK(expr)                         \
+  do {                                         \
+    int _rc = (expr);                          \
+    if (_rc != 0) return _rc;                  \
+  } while (0)
+
+#define SF_CUDA(expr)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SF_ERR_CUDA;                                                          \
+    }                                                                              \
+  } while (0)
+
+namespace {
+
+// ------------------------------------------------------------------ bind-time fp32 helper kernels
+__global__ void lora_merge_kernel(float* __restrict__ W, const float* __restrict__ A,
+                                  const float* __restrict__ Bm, int O, int I, int R) {
+  // W[o,i] += sum_r Bm[o,r] * A[r,i]      (…siglip.py:653-654, 749-751)
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long>(O) * I) return;
+  const int o = static_cast<int>(idx / I), i = static_cast<int>(idx % I);
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) acc += Bm[o * R + r] * A[r * I + i];
+  W[idx] += acc;
+}
+__global__ void matmul_nn_kernel(float* __restrict__ C, const float* __restrict__ A,
+                                 const float* __restrict__ Bm, int M, int N, int K) {
+  // C[m,n] = sum_k A[m,k] * Bm[k,n]   (one-off weight folding; correctness over speed)
+  __shared__ float as[16][17], bs[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    as[ty][tx] = (m < M && k0 + tx < K) ? A[static_cast<long>(m) * K + k0 + tx] : 0.f;
+    bs[ty][tx] = (k0 + ty < K && n < N) ? Bm[static_cast<long>(k0 + ty) * N + n] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += as[ty][k] * bs[k][tx];
+    __syncthreads();
+  }
+  if (m < M && n < N) C[static_cast<long>(m) * N + n] = acc;
+}
+__global__ void matvec_kernel(float* __restrict__ y, const float* __restrict__ W,
+                              const float* __restrict__ x, const float* __restrict__ b, int O, int I,
+                              float scale) {
+  // y[o] = scale * (sum_i W[o,i] x[i] + b[o]); one warp per output
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= O) return;
+  float acc = 0.f;
+  for (int i = lane; i < I; i += 32) acc += W[static_cast<long>(o) * I + i] * x[i];
+  acc = warp_sum(acc);
+  if (lane == 0) y[o] = scale * (acc + (b ? b[o] : 0.f));
+}
+
+struct Bump {
+  uint8_t* base = nullptr;
+  size_t size = 0, off = 0;
+  bool overflow = false;
+  void* take(size_t bytes) {
+    const size_t a = (off + 255) & ~static_cast<size_t>(255);
+    if (base == nullptr || a + bytes > size) {
+      overflow = true;
+      off = a + bytes;
+      return nullptr;
+    }
+    off = a + bytes;
+    return base + a;
+  }
+};
+
+struct LayerW {
+  void *t_qkv_w = nullptr, *t_out_w = nullptr, *t_dense_w = nullptr, *t_fold_w = nullptr;
+  void *s_qkv_w = nullptr, *s_out_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;
+  float *t_qkv_b = nullptr, *t_out_b = nullptr, *t_dense_b = nullptr, *t_fold_b = nullptr;
+  float *s_qkv_b = nullptr, *s_out_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
+  float *ln_t_g = nullptr, *ln_t_b = nullptr, *ln_s_g = nullptr, *ln_s_b = nullptr;
+  float *ln_a_g = nullptr, *ln_a_b = nullptr;
+  float* gate = nullptr;
+};
+
+}  // namespace
+
+struct sf_ctx {
+  sf_config cfg;
+  int device = 0;
+  int D = 0, H = 0, I = 0, L = 0, S0 = 0, Kp = 0;  // hidden, heads, mlp, layers, default sites, patch K
+  bool bound = false;
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<LayerW> layers;
+  void* patch_w = nullptr; float* patch_b = nullptr;
+  float* pos = nullptr;        // [S0, D]
+  float* time_emb = nullptr;   // [num_frames, D]
+  float* pos_alt = nullptr;    // user-provided interpolated table
+  int pos_alt_S = 0;
+  float *post_g = nullptr, *post_b = nullptr;
+  void *head_kv_w = nullptr, *head_out_w = nullptr, *head_fc1_w = nullptr, *head_fc2_w = nullptr;
+  float *head_kv_b = nullptr, *head_out_b = nullptr, *head_fc1_b = nullptr, *head_fc2_b = nullptr;
+  float *head_q = nullptr, *head_ln_g = nullptr, *head_ln_b = nullptr;
+};
+
+struct sf_kv {
+  sf_ctx* ctx = nullptr;
+  int B = 0, S = 0, cap = 0, seen = 0, horizon = 0;
+  uint8_t* mem = nullptr;
+  size_t layer_stride = 0;  // bytes between layers (K then V inside)
+  size_t kv_bytes = 0;      // bytes of one K (or V) block
+  void* k(int l) const { return mem + l * layer_stride; }
+  void* v(int l) const { return mem + l * layer_stride + kv_bytes; }
+};
+
+namespace {
+
+struct WsPlan {
+  void *ln, *qkv, *ctx, *tmp, *mlp;
+};
+
+size_t layer_ws_bytes(const sf_ctx* c, long M) {
+  const size_t es = 2;
+  const size_t D = c->D, I = c->I;
+  // ln[M,D] qkv[M,3D] ctx[M,D] tmp[M,D] mlp[M,I]  (+256 B alignment each)
+  return static_cast<size_t>(M) * (D + 3 * D + D + D + I) * es + 5 * 256;
+}
+
+int carve_layer_ws(const sf_ctx* c, long M, Bump& b, WsPlan& p) {
+  const size_t es = 2, D = c->D, I = c->I;
+  p.ln = b.take(M * D * es);
+  p.qkv = b.take(M * 3 * D * es);
+  p.ctx = b.take(M * D * es);
+  p.tmp = b.take(M * D * es);
+  p.mlp = b.take(M * I * es);
+  if (b.overflow) {
+    set_error("workspace too small: need at least %zu bytes, have %zu", b.off, b.size);
+    return SF_ERR_WORKSPACE;
+  }
+  return 0;
+}
+
+GemmEpilogue epi_bias(const float* bias) {
+  GemmEpilogue e;
+  e.bias = bias;
+  return e;
+}
+
+int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, int B, int T, int S,
+              sf_kv* kv, float* probs, const WsPlan& w) {
+  const LayerW& lw = c->layers[l];
+  const int D = c->D, I = c->I, H = c->H, dt = c->cfg.dtype;
+  const long M = static_cast<long>(B) * S * T;
+  const float eps = c->cfg.layer_norm_eps;
+  const float scale = 0.125f;  // head_dim**-0.5, head_dim == 64 (…siglip.py:512, 628)
+  const bool permute = T > 1;
+
+  // ---- temporal branch (…siglip.py:937-958): rows (b,n,t), T innermost => sites are contiguous
+  SF_CHECK(layernorm(st, dt, x_in, D, lw.ln_t_g, lw.ln_t_b, eps, w.ln, D, M, D, kRowIdentity, T, S));
+  SF_CHECK(gemm(st, dt, w.ln, D, lw.t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D, epi_bias(lw.t_qkv_b)));
+  if (kv) {
+    SF_CHECK(kv_append(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, B * S, H, T, kv->seen));
+    SF_CHECK(temporal_attention(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, w.ctx, D, B * S, H, T,
+                                kv->seen + T, kv->seen, c->cfg.causal_temporal, scale));
+  } else {
+    SF_CHECK(temporal_attention(st, dt, w.qkv, 3 * D, nullptr, nullptr, 0, w.ctx, D, B * S, H, T, T, 0,
+                                c->cfg.causal_temporal, scale));
+  }
+  {
+    GemmEpilogue e;
+    e.residual = x_in; e.ldr = D; e.gate = lw.gate;
+    if (c->cfg.fold_temporal_proj) {
+      e.bias = lw.t_fold_b;
+      SF_CHECK(gemm(st, dt, w.ctx, D, lw.t_fold_w, D, x_out, D, M, D, D, e));
+    } else {
+      SF_CHECK(gemm(st, dt, w.ctx, D, lw.t_out_w, D, w.tmp, D, M, D, D, epi_bias(lw.t_out_b)));
+      e.bias = lw.t_dense_b;
+      SF_CHECK(gemm(st, dt, w.tmp, D, lw.t_dense_w, D, x_out, D, M, D, D, e));
+    }
+  }
+  // ---- spatial branch (…siglip.py:960-996): QKV GEMM writes rows in (b,t,n) order, the out-proj
+  // epilogue maps them back onto the (b,n,t) residual — no permute copies.
+  SF_CHECK(layernorm(st, dt, x_out, D, lw.ln_s_g, lw.ln_s_b, eps, w.ln, D, M, D, kRowIdentity, T, S));
+  {
+    GemmEpilogue e = epi_bias(lw.s_qkv_b);
+    if (permute) { e.row_map = kRowBNTtoBTN; e.T = T; e.S = S; }
+    SF_CHECK(gemm(st, dt, w.ln, D, lw.s_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D, e));
+  }
+  SF_CHECK(spatial_attention(st, dt, w.qkv, 3 * D, w.ctx, D, B * T, H, S, scale, probs));
+  {
+    GemmEpilogue e = epi_bias(lw.s_out_b);
+    e.residual = x_out; e.ldr = D;
+    if (permute) { e.row_map = kRowBTNtoBNT; e.T = T; e.S = S; }
+    SF_CHECK(gemm(st, dt, w.ctx, D, lw.s_out_w, D, x_out, D, M, D, D, e));
+  }
+  // ---- MLP (…siglip.py:997-1000)
+  SF_CHECK(layernorm(st, dt, x_out, D, lw.ln_a_g, lw.ln_a_b, eps, w.ln, D, M, D, kRowIdentity, T, S));
+  {
+    GemmEpilogue e = epi_bias(lw.fc1_b);
+    e.act = c->cfg.hidden_act;
+    SF_CHECK(gemm(st, dt, w.ln, D, lw.fc1_w, D, w.mlp, I, M, I, D, e));
+  }
+  {
+    GemmEpilogue e = epi_bias(lw.fc2_b);
+    e.residual = x_out; e.ldr = D;
+    SF_CHECK(gemm(st, dt, w.mlp, I, lw.fc2_w, I, x_out, D, M, D, I, e));
+  }
+  return 0;
+}
+
+int run_embed(sf_ctx* c, cudaStream_t st, const void* pixels, int pix_dtype, int B, int T, int Hh, int Ww,
+              int time_off, int time_total, void* x_out, void* patches) {
+  const int P = c->cfg.patch_size, C = c->cfg.num_channels, D = c->D, dt = c->cfg.dtype;
+  const int S = (Hh / P) * (Ww / P);
+  const float* pos = nullptr;
+  if (S == c->S0 && Hh == Ww) pos = c->pos;                      // …siglip.py:384-385
+  else if (c->pos_alt && c->pos_alt_S == S) pos = c->pos_alt;
+  else {
+    set_error("resolution %dx%d (%d patches) needs an interpolated position table: call sf_set_pos_embed first",
+              Hh, Ww, S);
+    return SF_ERR_STATE;
+  }
+  const long M = static_cast<long>(B) * T * S;
+  SF_CHECK(im2col_patches(st, pix_dtype, pixels, dt, patches, B * T, C, Hh, Ww, P));
+  GemmEpilogue e = epi_bias(c->patch_b);
+  e.row_map = kRowBTNtoBNT; e.T = T; e.S = S;
+  e.pos = pos;
+  e.time_emb = c->time_emb; e.time_len = c->cfg.num_frames; e.time_total = time_total; e.time_off = time_off;
+  return gemm(st, dt, patches, c->Kp, c->patch_w, c->Kp, x_out, D, M, D, c->Kp, e);
+}
+
+size_t head_ws_bytes(const sf_ctx* c, long frames, long S) {
+  const size_t es = 2, D = c->D, I = c->I;
+  return static_cast<size_t>(frames) * S * 2 * D * es + static_cast<size_t>(frames) * (3 * D + I) * es + 6 * 256;
+}
+
+int run_head(sf_ctx* c, cudaStream_t st, const void* tokens, int frames, int S, void* pooled, Bump& b) {
+  const int D = c->D, I = c->I, H = c->H, dt = c->cfg.dtype;
+  const size_t es = 2;
+  const long M = static_cast<long>(frames) * S;
+  void* kvbuf = b.take(M * 2 * D * es);
+  void* pc = b.take(static_cast<size_t>(frames) * D * es);
+  void* r = b.take(static_cast<size_t>(frames) * D * es);
+  void* lnr = b.take(static_cast<size_t>(frames) * D * es);
+  void* hbuf = b.take(static_cast<size_t>(frames) * I * es);
+  if (b.overflow) {
+    set_error("workspace too small for the pooling head: need %zu bytes, have %zu", b.off, b.size);
+    return SF_ERR_WORKSPACE;
+  }
+  // K/V projection of every token (in_proj rows D..3D), probe attention, out_proj (…siglip.py:1146-1148)
+  SF_CHECK(gemm(st, dt, tokens, D, c->head_kv_w, D, kvbuf, 2 * D, M, 2 * D, D, epi_bias(c->head_kv_b)));
+  SF_CHECK(pool_attention(st, dt, kvbuf, 2 * D, c->head_q, pc, D, frames, H, S));
+  SF_CHECK(gemm(st, dt, pc, D, c->head_out_w, D, r, D, frames, D, D, epi_bias(c->head_out_b)));
+  // r + MLP(LN(r)) (…siglip.py:1150-1152)
+  SF_CHECK(layernorm(st, dt, r, D, c->head_ln_g, c->head_ln_b, c->cfg.layer_norm_eps, lnr, D, frames, D,
+                     kRowIdentity, 1, 1));
+  {
+    GemmEpilogue e = epi_bias(c->head_fc1_b);
+    e.act = c->cfg.hidden_act;
+    SF_CHECK(gemm(st, dt, lnr, D, c->head_fc1_w, D, hbuf, I, frames, I, D, e));
+  }
+  {
+    GemmEpilogue e = epi_bias(c->head_fc2_b);
+    e.residual = r; e.ldr = D;
+    SF_CHECK(gemm(st, dt, hbuf, I, c->head_fc2_w, I, pooled, D, frames, D, I, e));
+  }
+  return 0;
+}
+
+int check_shape(const sf_ctx* c, int B, int T, int Hh, int Ww) {
+  if (!c->bound) { set_error("weights not bound: call sf_bind_weights first"); return SF_ERR_STATE; }
+  const int P = c->cfg.patch_size;
+  if (B <= 0 || T <= 0 || Hh <= 0 || Ww <= 0 || (Hh % P) || (Ww % P)) {
+    set_error("bad input shape B=%d T=%d H=%d W=%d (patch %d)", B, T, Hh, Ww, P);
+    return SF_ERR_INVALID;
+  }
+  return 0;
+}
+
+int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int pix_dtype, int B, int T,
+                 int Hh, int Ww, void* last_hidden, void* pooler, void* const* hidden_states,
+                 void* const* attentions, void* ws, size_t ws_bytes) {
+  SF_CHECK(check_shape(c, B, T, Hh, Ww));
+  SF_CUDA(cudaSetDevice(c->device));
+  const int P = c->cfg.patch_size, D = c->D;
+  const int S = (Hh / P) * (Ww / P);
+  const long M = static_cast<long>(B) * T * S;
+  int time_off = 0, time_total = T;
+  if (kv) {
+    if (kv->B != B || kv->S != S) {
+      set_error("KV cache was created for B=%d S=%d, got B=%d S=%d", kv->B, kv->S, B, S);
+      return SF_ERR_INVALID;
+    }
+    if (kv->seen + T > kv->cap) {
+      set_error("KV cache overflow: %d cached + %d new frames > capacity %d", kv->seen, T, kv->cap);
+      return SF_ERR_STATE;
+    }
+    time_off = kv->seen;
+    time_total = kv->horizon > 0 ? kv->horizon : kv->seen + T;
+    if (time_total < kv->seen + T) time_total = kv->seen + T;
+  }
+  Bump b;
+  b.base = static_cast<uint8_t*>(ws);
+  b.size = ws_bytes;
+  void* x = nullptr;
+  if (!hidden_states) x = b.take(M * D * 2);
+  WsPlan w;
+  SF_CHECK(carve_layer_ws(c, M, b, w));
+  if (b.overflow) { set_error("workspace too small"); return SF_ERR_WORKSPACE; }
+  // the im2col operand aliases the (not yet used) MLP buffer: Kp <= I is checked at create time
+  void* cur = hidden_states ? hidden_states[0] : x;
+  SF_CHECK(run_embed(c, st, pixels, pix_dtype, B, T, Hh, Ww, time_off, time_total, cur, w.mlp));
+  for (int l = 0; l < c->L; ++l) {
+    void* nxt = hidden_states ? hidden_states[l + 1] : cur;
+    SF_CHECK(run_layer(c, st, l, cur, nxt, B, T, S, kv, attentions ? static_cast<float*>(attentions[l]) : nullptr, w));
+    cur = nxt;
+  }
+  if (kv) kv->seen += T;
+  // post_layernorm, written straight in (b,t,n) order == last_hidden_state (…siglip.py:1330-1346)
+  SF_CHECK(layernorm(st, c->cfg.dtype, cur, D, c->post_g, c->post_b, c->cfg.layer_norm_eps, last_hidden, D, M,
+                     D, T > 1 ? kRowBNTtoBTN : kRowIdentity, T, S));
+  if (pooler) {
+    // head scratch aliases the layer scratch (all layers are done)
+    Bump hb;
+    hb.base = static_cast<uint8_t*>(w.ln);
+    hb.size = static_cast<uint8_t*>(ws) + ws_bytes - static_cast<uint8_t*>(w.ln);
+    SF_CHECK(run_head(c, st, last_hidden, B * T, S, pooler, hb));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ weight binding
+struct Binder {
+  sf_ctx* c;
+  cudaStream_t st;
+  std::unordered_map<std::string, const sf_weight_desc*> map;
+  Bump arena;
+  float* scratch[3] = {nullptr, nullptr, nullptr};
+  size_t scratch_elems = 0;
+
+  const sf_weight_desc* find(const std::string& name, bool required = true) {
+    auto it = map.find(name);
+    if (it == map.end()) {
+      if (required) set_error("sf_bind_weights: missing tensor '%s'", name.c_str());
+      return nullptr;
+    }
+    return it->second;
+  }
+  static long numel(const sf_weight_desc* d) {
+    long n = 1;
+    for (int i = 0; i < d->ndim; ++i) n *= d->shape[i];
+    return n;
+  }
+  int expect(const sf_weight_desc* d, long n) {
+    if (numel(d) != n) {
+      set_error("sf_bind_weights: tensor '%s' has %ld elements, expected %ld", d->name, numel(d), n);
+      return SF_ERR_INVALID;
+    }
+    return 0;
+  }
+  // fp32 vector/table straight into the arena
+  int vec(const std::string& name, long n, float** out) {
+    const sf_weight_desc* d = find(name);
+    if (!d) return SF_ERR_INVALID;
+    SF_CHECK(expect(d, n));
+    *out = static_cast<float*>(arena.take(n * sizeof(float)));
+    if (!*out) { set_error("sf_bind_weights: arena exhausted at '%s'", name.c_str()); return SF_ERR_STATE; }
+    return cast(st, d->dtype, d->data, kF32, *out, n);
+  }
+  // matrix in activation dtype
+  int mat(const std::string& name, long rows, long cols, void** out) {
+    const sf_weight_desc* d = find(name);
+    if (!d) return SF_ERR_INVALID;
+    SF_CHECK(expect(d, rows * cols));
+    *out = arena.take(rows * cols * 2);
+    if (!*out) { set_error("sf_bind_weights: arena exhausted at '%s'", name.c_str()); return SF_ERR_STATE; }
+    return cast(st, d->dtype, d->data, c->cfg.dtype, *out, rows * cols);
+  }
+  int to_scratch(int slot, const sf_weight_desc* d, long n) {
+    if (static_cast<size_t>(n) > scratch_elems) { set_error("bind scratch too small"); return SF_ERR_INVALID; }
+    return cast(st, d->dtype, d->data, kF32, scratch[slot], n);
+  }
+  // W (+ lora_b . lora_a) in activation dtype
+  int mat_lora(const std::string& wname, const std::string& aname, const std::string& bname, long O, long I,
+               void** out) {
+    const sf_weight_desc* a = find(aname, false);
+    const sf_weight_desc* bm = find(bname, false);
+    if (!a || !bm) return mat(wname, O, I, out);
+    const sf_weight_desc* wd = find(wname);
+    if (!wd) return SF_ERR_INVALID;
+    SF_CHECK(expect(wd, O * I));
+    const long R = numel(a) / I;
+    SF_CHECK(expect(a, R * I));
+    SF_CHECK(expect(bm, O * R));
+    SF_CHECK(to_scratch(0, wd, O * I));
+    SF_CHECK(to_scratch(1, a, R * I));
+    SF_CHECK(to_scratch(2, bm, O * R));
+    const long total = O * I;
+    lora_merge_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(scratch[0], scratch[1], scratch[2],
+                                                                                  static_cast<int>(O), static_cast<int>(I),
+                                                                                  static_cast<int>(R));
+    count_launch();
+    *out = arena.take(O * I * 2);
+    return cast(st, kF32, scratch[0], c->cfg.dtype, *out, O * I);
+  }
+};
+
+size_t arena_bytes_for(const sf_ctx* c) {
+  const size_t D = c->D, I = c->I, L = c->L, K = c->Kp, S0 = c->S0, F = c->cfg.num_frames;
+  size_t per_layer = (3 * D * D + D * D * 3 + 3 * D * D + D * D + 2 * D * I) * 2  // matrices (incl. folded)
+                     + (3 * D + D * 3 + 3 * D + D + I + D + 6 * D + 1) * 4 + 40 * 256;
+  size_t other = D * K * 2 + (D + S0 * D + F * D + 2 * D) * 4 + (2 * D * D + D * D + 2 * D * I) * 2 +
+                 (2 * D + D + I + D + D + 2 * D) * 4 + 40 * 256;
+  return per_layer * L + other + (1 << 20);
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+const char* sf_last_error(void) { return last_error(); }
+const char* sf_version(void) { return "streamformer_b200 0.1 (sm_100a)"; }
+uint64_t sf_launch_count(void) { return launch_count(); }
+
+int sf_create(const sf_config* cfg, int device, sf_ctx** out) {
+  if (!cfg || !out) { set_error("sf_create: null argument"); return SF_ERR_INVALID; }
+  if (cfg->hidden_size % cfg->num_attention_heads || cfg->hidden_size / cfg->num_attention_heads != 64) {
+    set_error("sf_create: head dim must be 64 (hidden %d / heads %d)", cfg->hidden_size, cfg->num_attention_heads);
+    return SF_ERR_INVALID;
+  }
+  if (cfg->dtype != SF_BF16 && cfg->dtype != SF_F16) { set_error("sf_create: dtype must be bf16 or f16"); return SF_ERR_INVALID; }
+  if (cfg->hidden_act != SF_ACT_GELU && cfg->hidden_act != SF_ACT_GELU_TANH) {
+    set_error("sf_create: hidden_act must be gelu or gelu_pytorch_tanh");
+    return SF_ERR_INVALID;
+  }
+  const int Kp = cfg->num_channels * cfg->patch_size * cfg->patch_size;
+  if ((cfg->patch_size % 8) || (cfg->image_size % cfg->patch_size) || (cfg->hidden_size % 8) ||
+      (cfg->intermediate_size % 8) || Kp > cfg->intermediate_size) {
+    set_error("sf_create: unsupported geometry (patch %d image %d hidden %d mlp %d)", cfg->patch_size,
+              cfg->image_size, cfg->hidden_size, cfg->intermediate_size);
+    return SF_ERR_INVALID;
+  }
+  SF_CUDA(cudaSetDevice(device));
+  int major = 0;
+  SF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    set_error("sf_create: device %d is sm_%dx; this library contains sm_100a code only", device, major);
+    return SF_ERR_CUDA;
+  }
+  sf_ctx* c = new sf_ctx();
+  c->cfg = *cfg;
+  c->device = device;
+  c->D = cfg->hidden_size; c->H = cfg->num_attention_heads; c->I = cfg->intermediate_size;
+  c->L = cfg->num_hidden_layers; c->Kp = Kp;
+  const int g = cfg->image_size / cfg->patch_size;
+  c->S0 = g * g;
+  c->layers.resize(c->L);
+  *out = c;
+  return 0;
+}
+
+int sf_destroy(sf_ctx* c) {
+  if (!c) return 0;
+  if (c->arena) cudaFree(c->arena);
+  if (c->pos_alt) cudaFree(c->pos_alt);
+  delete c;
+  return 0;
+}
+
+int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
+  if (!c || !w) { set_error("sf_bind_weights: null argument"); return SF_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SF_CUDA(cudaSetDevice(c->device));
+  Binder b;
+  b.c = c; b.st = st;
+  for (int i = 0; i < n; ++i) {
+    std::string name = w[i].name ? w[i].name : "";
+    if (name.rfind("timesformer.", 0) == 0) name = name.substr(12);
+    b.map[name] = &w[i];
+  }
+  if (!c->arena) {
+    c->arena_bytes = arena_bytes_for(c);
+    SF_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
+  }
+  b.arena.base = c->arena; b.arena.size = c->arena_bytes;
+  const long D = c->D, I = c->I, K = c->Kp;
+  b.scratch_elems = static_cast<size_t>(3 * D > I ? 3 * D : I) * D;
+  if (b.scratch_elems < static_cast<size_t>(D * K)) b.scratch_elems = D * K;
+  float* scratch_mem = nullptr;
+  SF_CUDA(cudaMalloc(&scratch_mem, b.scratch_elems * 3 * sizeof(float)));
+  for (int i = 0; i < 3; ++i) b.scratch[i] = scratch_mem + i * b.scratch_elems;
+
+  auto body = [&]() -> int {
+    SF_CHECK(b.mat("embeddings.patch_embeddings.projection.weight", D, K, &c->patch_w));
+    SF_CHECK(b.vec("embeddings.patch_embeddings.projection.bias", D, &c->patch_b));
+    SF_CHECK(b.vec("embeddings.position_embeddings", static_cast<long>(c->S0) * D, &c->pos));
+    SF_CHECK(b.vec("embeddings.time_embeddings", static_cast<long>(c->cfg.num_frames) * D, &c->time_emb));
+    for (int l = 0; l < c->L; ++l) {
+      LayerW& lw = c->layers[l];
+      const std::string p = "encoder.layer." + std::to_string(l) + ".";
+      SF_CHECK(b.vec(p + "temporal_attention_gating", 1, &lw.gate));
+      SF_CHECK(b.vec(p + "temporal_layernorm.weight", D, &lw.ln_t_g));
+      SF_CHECK(b.vec(p + "temporal_layernorm.bias", D, &lw.ln_t_b));
+      SF_CHECK(b.vec(p + "layernorm_before.weight", D, &lw.ln_s_g));
+      SF_CHECK(b.vec(p + "layernorm_before.bias", D, &lw.ln_s_b));
+      SF_CHECK(b.vec(p + "layernorm_after.weight", D, &lw.ln_a_g));
+      SF_CHECK(b.vec(p + "layernorm_after.bias", D, &lw.ln_a_b));
+      SF_CHECK(b.mat(p + "temporal_attention.attention.qkv.weight", 3 * D, D, &lw.t_qkv_w));
+      SF_CHECK(b.vec(p + "temporal_attention.attention.qkv.bias", 3 * D, &lw.t_qkv_b));
+      SF_CHECK(b.mat(p + "temporal_attention.output.dense.weight", D, D, &lw.t_out_w));
+      SF_CHECK(b.vec(p + "temporal_attention.output.dense.bias", D, &lw.t_out_b));
+      SF_CHECK(b.mat(p + "temporal_dense.weight", D, D, &lw.t_dense_w));
+      SF_CHECK(b.vec(p + "temporal_dense.bias", D, &lw.t_dense_b));
+      {
+        // folded projection: W_f = W_td . W_o ; b_f = W_td . b_o + b_td   (fp32, then one rounding)
+        const sf_weight_desc* wo = b.find(p + "temporal_attention.output.dense.weight");
+        const sf_weight_desc* wtd = b.find(p + "temporal_dense.weight");
+        SF_CHECK(b.to_scratch(0, wtd, D * D));
+        SF_CHECK(b.to_scratch(1, wo, D * D));
+        dim3 grid(static_cast<unsigned>((D + 15) / 16), static_cast<unsigned>((D + 15) / 16)), blk(16, 16);
+        matmul_nn_kernel<<<grid, blk, 0, st>>>(b.scratch[2], b.scratch[0], b.scratch[1], static_cast<int>(D),
+                                               static_cast<int>(D), static_cast<int>(D));
+        count_launch();
+        lw.t_fold_w = b.arena.take(D * D * 2);
+        SF_CHECK(cast(st, kF32, b.scratch[2], c->cfg.dtype, lw.t_fold_w, D * D));
+        lw.t_fold_b = static_cast<float*>(b.arena.take(D * sizeof(float)));
+        matvec_kernel<<<static_cast<unsigned>((D + 7) / 8), 256, 0, st>>>(lw.t_fold_b, b.scratch[0], lw.t_out_b,
+                                                                          lw.t_dense_b, static_cast<int>(D),
+                                                                          static_cast<int>(D), 1.0f);
+        count_launch();
+      }
+      SF_CHECK(b.mat_lora(p + "attention.attention.qkv.weight", p + "attention.attention.qkv_lora_a.weight",
+                          p + "attention.attention.qkv_lora_b.weight", 3 * D, D, &lw.s_qkv_w));
+      SF_CHECK(b.vec(p + "attention.attention.qkv.bias", 3 * D, &lw.s_qkv_b));
+      SF_CHECK(b.mat_lora(p + "attention.output.dense.weight", p + "attention.output.dense_lora_a.weight",
+                          p + "attention.output.dense_lora_b.weight", D, D, &lw.s_out_w));
+      SF_CHECK(b.vec(p + "attention.output.dense.bias", D, &lw.s_out_b));
+      SF_CHECK(b.mat(p + "intermediate.dense.weight", I, D, &lw.fc1_w));
+      SF_CHECK(b.vec(p + "intermediate.dense.bias", I, &lw.fc1_b));
+      SF_CHECK(b.mat(p + "output.dense.weight", D, I, &lw.fc2_w));
+      SF_CHECK(b.vec(p + "output.dense.bias", D, &lw.fc2_b));
+    }
+    SF_CHECK(b.vec("post_layernorm.weight", D, &c->post_g));
+    SF_CHECK(b.vec("post_layernorm.bias", D, &c->post_b));
+    // pooling head: in_proj rows [0,D) = W_q, [D,3D) = W_k;W_v (…siglip.py:1135-1137)
+    {
+      const sf_weight_desc* ipw = b.find("head.attention.in_proj_weight");
+      const sf_weight_desc* ipb = b.find("head.attention.in_proj_bias");
+      const sf_weight_desc* probe = b.find("head.probe");
+      if (!ipw || !ipb || !probe) return SF_ERR_INVALID;
+      SF_CHECK(b.expect(ipw, 3 * D * D));
+      SF_CHECK(b.expect(ipb, 3 * D));
+      SF_CHECK(b.expect(probe, D));
+      const size_t es_in = dtype_size(ipw->dtype);
+      c->head_kv_w = b.arena.take(2 * D * D * 2);
+      SF_CHECK(cast(st, ipw->dtype, static_cast<const uint8_t*>(ipw->data) + static_cast<size_t>(D) * D * es_in,
+                    c->cfg.dtype, c->head_kv_w, 2 * D * D));
+      c->head_kv_b = static_cast<float*>(b.arena.take(2 * D * sizeof(float)));
+      SF_CHECK(cast(st, ipb->dtype, static_cast<const uint8_t*>(ipb->data) + static_cast<size_t>(D) * dtype_size(ipb->dtype),
+                    kF32, c->head_kv_b, 2 * D));
+      // q = (W_q probe + b_q) / sqrt(64), constant per model
+      SF_CHECK(b.to_scratch(0, ipw, D * D));   // first D rows only are used
+      SF_CHECK(cast(st, ipb->dtype, ipb->data, kF32, b.scratch[1], D));
+      SF_CHECK(cast(st, probe->dtype, probe->data, kF32, b.scratch[2], D));
+      c->head_q = static_cast<float*>(b.arena.take(D * sizeof(float)));
+      matvec_kernel<<<static_cast<unsigned>((D + 7) / 8), 256, 0, st>>>(c->head_q, b.scratch[0], b.scratch[2],
+                                                                        b.scratch[1], static_cast<int>(D),
+                                                                        static_cast<int>(D), 0.125f);
+      count_launch();
+    }
+    SF_CHECK(b.mat("head.attention.out_proj.weight", D, D, &c->head_out_w));
+    SF_CHECK(b.vec("head.attention.out_proj.bias", D, &c->head_out_b));
+    SF_CHECK(b.vec("head.layernorm.weight", D, &c->head_ln_g));
+    SF_CHECK(b.vec("head.layernorm.bias", D, &c->head_ln_b));
+    SF_CHECK(b.mat("head.mlp.fc1.weight", I, D, &c->head_fc1_w));
+    SF_CHECK(b.vec("head.mlp.fc1.bias", I, &c->head_fc1_b));
+    SF_CHECK(b.mat("head.mlp.fc2.weight", D, I, &c->head_fc2_w));
+    SF_CHECK(b.vec("head.mlp.fc2.bias", D, &c->head_fc2_b));
+    if (b.arena.overflow) { set_error("sf_bind_weights: internal arena too small (%zu > %zu)", b.arena.off, b.arena.size); return SF_ERR_STATE; }
+    return 0;
+  };
+  int rc = body();
+  cudaError_t e = cudaStreamSynchronize(st);  // scratch is freed below; binding is not a hot path
+  cudaFree(scratch_mem);
+  if (rc) return rc;
+  if (e != cudaSuccess) { set_error("sf_bind_weights: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
+  c->bound = true;
+  return 0;
+}
+
+int sf_set_pos_embed(sf_ctx* c, void* stream, const float* pos, int S) {
+  if (!c || !pos || S <= 0) { set_error("sf_set_pos_embed: bad argument"); return SF_ERR_INVALID; }
+  SF_CUDA(cudaSetDevice(c->device));
+  if (c->pos_alt_S != S) {
+    if (c->pos_alt) { cudaFree(c->pos_alt); c->pos_alt = nullptr; }
+    SF_CUDA(cudaMalloc(&c->pos_alt, static_cast<size_t>(S) * c->D * sizeof(float)));
+    c->pos_alt_S = S;
+  }
+  SF_CUDA(cudaMemcpyAsync(c->pos_alt, pos, static_cast<size_t>(S) * c->D * sizeof(float), cudaMemcpyDeviceToDevice,
+                          static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sf_workspace_bytes(const sf_ctx* c, int B, int T, int Hh, int Ww, size_t* out) {
+  if (!c || !out) { set_error("sf_workspace_bytes: null argument"); return SF_ERR_INVALID; }
+  const int P = c->cfg.patch_size;
+  const long S = static_cast<long>(Hh / P) * (Ww / P);
+  const long M = static_cast<long>(B) * T * S;
+  size_t layer = static_cast<size_t>(M) * c->D * 2 + 256 + layer_ws_bytes(c, M);
+  size_t head = static_cast<size_t>(M) * c->D * 2 + 256 + head_ws_bytes(c, static_cast<long>(B) * T, S);
+  *out = (layer > head ? layer : head) + 4096;
+  return 0;
+}
+
+int sf_forward(sf_ctx* c, void* stream, const void* pixels, int pixels_dtype, int B, int T, int Hh, int Ww,
+               void* last_hidden, void* pooler, void* const* hidden_states, void* const* attentions,
+               void* workspace, size_t workspace_bytes) {
+  if (!c || !pixels || !last_hidden) { set_error("sf_forward: null argument"); return SF_ERR_INVALID; }
+  return forward_impl(c, static_cast<cudaStream_t>(stream), nullptr, pixels, pixels_dtype, B, T, Hh, Ww, last_hidden,
+                      pooler, hidden_states, attentions, workspace, workspace_bytes);
+}
+
+int sf_kv_create(sf_ctx* c, int B, int S, int max_frames, int time_horizon, sf_kv** out) {
+  if (!c || !out || B <= 0 || S <= 0 || max_frames <= 0) { set_error("sf_kv_create: bad argument"); return SF_ERR_INVALID; }
+  SF_CUDA(cudaSetDevice(c->device));
+  sf_kv* kv = new sf_kv();
+  kv->ctx = c; kv->B = B; kv->S = S; kv->cap = max_frames; kv->horizon = time_horizon;
+  kv->kv_bytes = static_cast<size_t>(B) * S * c->H * max_frames * 64 * 2;
+  kv->layer_stride = 2 * kv->kv_bytes;
+  cudaError_t e = cudaMalloc(&kv->mem, kv->layer_stride * c->L);
+  if (e != cudaSuccess) {
+    set_error("sf_kv_create: cudaMalloc(%zu bytes) failed: %s", kv->layer_stride * c->L, cudaGetErrorString(e));
+    delete kv;
+    return SF_ERR_CUDA;
+  }
+  *out = kv;
+  return 0;
+}
+int sf_kv_reset(sf_kv* kv) { if (kv) kv->seen = 0; return 0; }
+int sf_kv_destroy(sf_kv* kv) {
+  if (!kv) return 0;
+  if (kv->mem) cudaFree(kv->mem);
+  delete kv;
+  return 0;
+}
+int sf_kv_seq_len(const sf_kv* kv) { return kv ? kv->seen : 0; }
+int sf_kv_capacity(const sf_kv* kv) { return kv ? kv->cap : 0; }
+
+int sf_forward_stream(sf_ctx* c, void* stream, sf_kv* kv, const void* pixels, int pixels_dtype, int B, int T_new,
+                      int Hh, int Ww, void* last_hidden, void* pooler, void* const* hidden_states, void* workspace,
+                      size_t workspace_bytes) {
+  if (!c || !kv || !pixels || !last_hidden) { set_error("sf_forward_stream: null argument"); return SF_ERR_INVALID; }
+  return forward_impl(c, static_cast<cudaStream_t>(stream), kv, pixels, pixels_dtype, B, T_new, Hh, Ww, last_hidden,
+                      pooler, hidden_states, nullptr, workspace, workspace_bytes);
+}
+
+int sf_embed_forward(sf_ctx* c, void* stream, const void* pixels, int pixels_dtype, int B, int T, int Hh, int Ww,
+                     int time_off, int time_total, void* x_out, void* workspace, size_t workspace_bytes) {
+  if (!c || !pixels || !x_out) { set_error("sf_embed_forward: null argument"); return SF_ERR_INVALID; }
+  SF_CHECK(check_shape(c, B, T, Hh, Ww));
+  const int P = c->cfg.patch_size;
+  const long M = static_cast<long>(B) * T * (Hh / P) * (Ww / P);
+  Bump b;
+  b.base = static_cast<uint8_t*>(workspace); b.size = workspace_bytes;
+  void* patches = b.take(static_cast<size_t>(M) * c->Kp * 2);
+  if (b.overflow) { set_error("sf_embed_forward: workspace too small (need %zu)", b.off); return SF_ERR_WORKSPACE; }
+  if (time_total < time_off + T) time_total = time_off + T;
+  return run_embed(c, static_cast<cudaStream_t>(stream), pixels, pixels_dtype, B, T, Hh, Ww, time_off, time_total, x_out,
+                   patches);
+}
+
+int sf_layer_forward(sf_ctx* c, void* stream, int layer, const void* x_in, void* x_out, int B, int T, int S, sf_kv* kv,
+                     float* attn_probs, void* workspace, size_t workspace_bytes) {
+  if (!c || !x_in || !x_out) { set_error("sf_layer_forward: null argument"); return SF_ERR_INVALID; }
+  if (!c->bound) { set_error("weights not bound"); return SF_ERR_STATE; }
+  if (layer < 0 || layer >= c->L) { set_error("sf_layer_forward: layer %d out of range", layer); return SF_ERR_INVALID; }
+  Bump b;
+  b.base = static_cast<uint8_t*>(workspace); b.size = workspace_bytes;
+  WsPlan w;
+  SF_CHECK(carve_layer_ws(c, static_cast<long>(B) * T * S, b, w));
+  return run_layer(c, static_cast<cudaStream_t>(stream), layer, x_in, x_out, B, T, S, kv, attn_probs, w);
+}
+
+int sf_final_norm(sf_ctx* c, void* stream, const void* x, int B, int T, int S, void* last_hidden) {
+  if (!c || !x || !last_hidden) { set_error("sf_final_norm: null argument"); return SF_ERR_INVALID; }
+  if (!c->bound) { set_error("weights not bound"); return SF_ERR_STATE; }
+  return layernorm(static_cast<cudaStream_t>(stream), c->cfg.dtype, x, c->D, c->post_g, c->post_b, c->cfg.layer_norm_eps,
+                   last_hidden, c->D, static_cast<long>(B) * T * S, c->D, T > 1 ? kRowBNTtoBTN : kRowIdentity, T, S);
+}
+
+int sf_head_forward(sf_ctx* c, void* stream, const void* tokens, int frames, int S, void* pooled, void* workspace,
+                    size_t workspace_bytes) {
+  if (!c || !tokens || !pooled) { set_error("sf_head_forward: null argument"); return SF_ERR_INVALID; }
+  if (!c->bound) { set_error("weights not bound"); return SF_ERR_STATE; }
+  Bump b;
+  b.base = static_cast<uint8_t*>(workspace); b.size = workspace_bytes;
+  return run_head(c, static_cast<cudaStream_t>(stream), tokens, frames, S, pooled, b);
+}
+
+// ---- single kernels
+int sf_op_gemm(void* stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N,
+               int K, const sf_gemm_epilogue* e) {
+  GemmEpilogue g;
+  if (e) {
+    g.bias = e->bias; g.act = e->act; g.residual = e->residual; g.ldr = e->ldr; g.gate = e->gate;
+    g.row_map = e->row_map; g.T = e->T > 0 ? e->T : 1; g.S = e->S > 0 ? e->S : 1;
+    g.pos = e->pos; g.time_emb = e->time_emb; g.time_len = e->time_len; g.time_total = e->time_total;
+    g.time_off = e->time_off;
+  }
+  return gemm(static_cast<cudaStream_t>(stream), dtype, A, lda, W, ldw, out, ldo, M, N, K, g);
+}
+int sf_op_layernorm(void* stream, int dtype, const void* x, int ldx, const float* gamma, const float* beta, float eps,
+                    void* y, int ldy, int M, int D, int row_map, int T, int S) {
+  return layernorm(static_cast<cudaStream_t>(stream), dtype, x, ldx, gamma, beta, eps, y, ldy, M, D, row_map,
+                   T > 0 ? T : 1, S > 0 ? S : 1);
+}
+int sf_op_im2col(void* stream, int pix_dtype, const void* pixels, int act_dtype, void* out, int BT, int C, int Hh, int Ww,
+                 int P) {
+  return im2col_patches(static_cast<cudaStream_t>(stream), pix_dtype, pixels, act_dtype, out, BT, C, Hh, Ww, P);
+}
+int sf_op_temporal_attention(void* stream, int dtype, const void* qkv, int ld_qkv, const void* kcache, const void* vcache,
+                             int Tcap, void* out, int ld_out, int sites, int heads, int Tq, int Tk, int q_off, int causal,
+                             float scale) {
+  return temporal_attention(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, kcache, vcache, Tcap, out, ld_out, sites,
+                            heads, Tq, Tk, q_off, causal, scale);
+}
+int sf_op_kv_append(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache, int Tcap, int sites,
+                    int heads, int Tq, int pos0) {
+  return kv_append(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, kcache, vcache, Tcap, sites, heads, Tq, pos0);
+}
+int sf_op_spatial_attention(void* stream, int dtype, const void* qkv, int ld_qkv, void* out, int ld_out, int frames,
+                            int heads, int S, float scale, float* probs) {
+  return spatial_attention(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, out, ld_out, frames, heads, S, scale,
+                           probs);
+}
+int sf_op_pool_attention(void* stream, int dtype, const void* kv, int ld_kv, const float* q, void* out, int ld_out,
+                         int frames, int heads, int S) {
+  return pool_attention(static_cast<cudaStream_t>(stream), dtype, kv, ld_kv, q, out, ld_out, frames, heads, S);
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// sf_kernels.h — internal launcher interface between the StreamFormer runtime (runtime.cu /
+// c_abi.cu) and the hand-written sm_100a kernels. All launchers are asynchronous on `stream`,
+// never allocate, and return 0 or a negative sf_status.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace sf {
+
+enum DType : int { kBF16 = 0, kF16 = 1, kF32 = 2 };
+inline size_t dtype_size(int dt) { return dt == kF32 ? 4 : 2; }
+
+enum RowMap : int {
+  kRowIdentity = 0,
+  kRowBTNtoBNT = 1,  // GEMM row m=(b*T+t)*S+n  -> output row (b*S+n)*T+t
+  kRowBNTtoBTN = 2,  // GEMM row m=(b*S+n)*T+t  -> output row (b*T+t)*S+n
+};
+enum Act : int { kActNone = 0, kActGeluErf = 1, kActGeluTanh = 2 };
+
+// Epilogue of  out[r, :] = f(A[m, :] . W^T)  with r = row_map(m).
+//   v = acc + bias ; v = act(v) ; v += pos[n] + time[tidx(t)] ; v = residual[r] + tanh(*gate) * v
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N] fp32
+  int act = kActNone;
+  const void* residual = nullptr;   // activation dtype, row stride ldr, indexed by OUTPUT row
+  int ldr = 0;
+  const float* gate = nullptr;      // device scalar (pre-tanh); nullptr => scale 1
+  int row_map = kRowIdentity;
+  int T = 1;                        // frames per clip   (row_map / pos / time decomposition)
+  int S = 1;                        // sites (patches) per frame
+  const float* pos = nullptr;       // [S, N] fp32, added per site n   (rows in (b,t,n) order)
+  const float* time_emb = nullptr;  // [time_len, N] fp32, added per frame t
+  int time_len = 0;                 // rows in the time table (config.num_frames)
+  int time_total = 0;               // total frames the table is stretched over (>= time_off+T)
+  int time_off = 0;                 // frames already seen (streaming)
+};
+
+// C[M,N] = A[M,K] . W[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+// A: row-major, leading dim lda (elements); W: row-major [N,K], leading dim ldw; out leading dim ldo.
+// Requirements: K % 8 == 0, N % 8 == 0, lda/ldw/ldo/ldr % 8 == 0, 16-byte aligned pointers.
+int gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out,
+         int ldo, int M, int N, int K, const GemmEpilogue& epi);
+
+// y = LayerNorm(x) * gamma + beta over the last dim D (fp32 statistics, biased variance).
+// row_map as in GemmEpilogue (input row m -> output row r), T/S for the decomposition.
+int layernorm(cudaStream_t stream, int dtype, const void* x, int ldx, const float* gamma,
+              const float* beta, float eps, void* y, int ldy, int M, int D, int row_map, int T,
+              int S);
+
+// pixels [BT, C, H, W] (pix_dtype: bf16/f16/f32) -> patch-major A[(bt*S + n), C*P*P] in act dtype,
+// K ordered (c, kh, kw) like Conv2d.weight.reshape(D, -1).
+int im2col_patches(cudaStream_t stream, int pix_dtype, const void* pixels, int act_dtype, void* out,
+                   int BT, int C, int H, int W, int P);
+
+// Temporal attention over frames, one (site, head) per warp task.
+//   q rows: qkv[(site*Tq + i), h*64 + d]                (row stride ld_qkv; q at col 0)
+//   keys/values: if kcache == nullptr, K/V come from the same qkv buffer (cols D.., 2D..) with
+//   Tk == Tq rows per site; else from the cache [site][head][Tcap][64] with Tk valid rows
+//   (the new rows must already be appended).  q row i attends to keys j <= q_off + i when
+//   causal, all Tk keys otherwise.  out[(site*Tq + i), h*64 + d], row stride ld_out.
+int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, const void* kcache,
+                       const void* vcache, int Tcap, void* out, int ld_out, int sites, int heads,
+                       int Tq, int Tk, int q_off, int causal, float scale);
+
+// Append the K and V slices of qkv (rows (site*Tq + i)) into cache[site][head][pos0 + i][64].
+int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
+              int Tcap, int sites, int heads, int Tq, int pos0);
+
+// Spatial attention inside each frame: qkv rows (frame*S + n), q|k|v column blocks of width
+// heads*64; full (non-causal) softmax over the S keys; out rows (frame*S + n).
+// probs (optional, fp32 [frames, heads, S, S]) receives the attention probabilities.
+int spatial_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* out,
+                      int ld_out, int frames, int heads, int S, float scale, float* probs);
+
+// Attention-pooling core of the SigLIP head: for each frame and head, softmax_n(q_h . K[n,h]) V[n,h].
+//   kv rows (frame*S + n): [K (heads*64) | V (heads*64)], q: [heads*64] fp32 (already scaled).
+//   out [frames, heads*64] in act dtype.
+int pool_attention(cudaStream_t stream, int dtype, const void* kv, int ld_kv, const float* q,
+                   void* out, int ld_out, int frames, int heads, int S);
+
+// out = cast(in)  (weight / bias packing helpers; n elements)
+int cast(cudaStream_t stream, int src_dtype, const void* src, int dst_dtype, void* dst, size_t n);
+
+// Number of kernel launches issued by this library since load (all launchers increment it).
+uint64_t launch_count();
+void count_launch(int n = 1);
+
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+}  // namespace sf

@@ -1,0 +1,123 @@
+"""torch.Tensor wrappers over the single-kernel C-ABI entry points (sf_op_*).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every computation happens in
+the hand-written sm_100a kernels.  Every wrapper requires CUDA tensors and raises otherwise.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _native as N
+
+_DT = {torch.bfloat16: N.SF_BF16, torch.float16: N.SF_F16, torch.float32: N.SF_F32}
+
+
+def sf_dtype(t: torch.dtype) -> int:
+    if t not in _DT:
+        raise TypeError(f"unsupported dtype {t}; the encoder runs in bfloat16 or float16")
+    return _DT[t]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise N.NativeError("streamformer_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = N.SF_ACT_NONE,
+         residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+         row_map: int = N.SF_ROW_IDENTITY, T: int = 1, S: int = 1, pos: Optional[torch.Tensor] = None,
+         time_emb: Optional[torch.Tensor] = None, time_total: int = 0, time_off: int = 0,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = epilogue(a[m] @ w.T); a [M,K], w [N,K] (nn.Linear layout), fp32 bias/pos/time/gate."""
+    _req(a, w, bias, residual, gate, pos, time_emb, out)
+    M, K = a.shape
+    Nn = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, Nn, dtype=a.dtype, device=a.device)
+    e = N.SfGemmEpilogue()
+    e.bias = _p(bias); e.act = act
+    e.residual = _p(residual); e.ldr = residual.stride(0) if residual is not None else 0
+    e.gate = _p(gate); e.row_map = row_map; e.T = T; e.S = S
+    e.pos = _p(pos); e.time_emb = _p(time_emb)
+    e.time_len = time_emb.shape[0] if time_emb is not None else 0
+    e.time_total = time_total; e.time_off = time_off
+    for t in (bias, gate, pos, time_emb):
+        assert t is None or t.dtype == torch.float32
+    N.check(N.load().sf_op_gemm(_stream(), sf_dtype(a.dtype), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
+                                out.data_ptr(), out.stride(0), M, Nn, K, e), "sf_op_gemm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, row_map: int = 0, T: int = 1,
+              S: int = 1) -> torch.Tensor:
+    _req(x, gamma, beta)
+    M, D = x.shape
+    y = torch.empty(M, D, dtype=x.dtype, device=x.device)
+    N.check(N.load().sf_op_layernorm(_stream(), sf_dtype(x.dtype), x.data_ptr(), x.stride(0), gamma.data_ptr(),
+                                     beta.data_ptr(), eps, y.data_ptr(), y.stride(0), M, D, row_map, T, S),
+            "sf_op_layernorm")
+    return y
+
+
+def im2col(pixels: torch.Tensor, patch: int, act_dtype: torch.dtype) -> torch.Tensor:
+    _req(pixels)
+    BT, Cc, H, W = pixels.shape
+    S = (H // patch) * (W // patch)
+    out = torch.empty(BT * S, Cc * patch * patch, dtype=act_dtype, device=pixels.device)
+    N.check(N.load().sf_op_im2col(_stream(), sf_dtype(pixels.dtype), pixels.data_ptr(), sf_dtype(act_dtype),
+                                  out.data_ptr(), BT, Cc, H, W, patch), "sf_op_im2col")
+    return out
+
+
+def temporal_attention(qkv: torch.Tensor, sites: int, heads: int, Tq: int, causal: bool, scale: float,
+                       kcache: Optional[torch.Tensor] = None, vcache: Optional[torch.Tensor] = None, Tk: int = 0,
+                       q_off: int = 0) -> torch.Tensor:
+    _req(qkv, kcache, vcache)
+    D = heads * 64
+    out = torch.empty(sites * Tq, D, dtype=qkv.dtype, device=qkv.device)
+    Tcap = kcache.shape[2] if kcache is not None else 0
+    N.check(N.load().sf_op_temporal_attention(_stream(), sf_dtype(qkv.dtype), qkv.data_ptr(), qkv.stride(0),
+                                              _p(kcache), _p(vcache), Tcap, out.data_ptr(), out.stride(0), sites,
+                                              heads, Tq, Tk if kcache is not None else Tq, q_off, int(causal), scale),
+            "sf_op_temporal_attention")
+    return out
+
+
+def kv_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, sites: int, heads: int, Tq: int,
+              pos0: int) -> None:
+    _req(qkv, kcache, vcache)
+    N.check(N.load().sf_op_kv_append(_stream(), sf_dtype(qkv.dtype), qkv.data_ptr(), qkv.stride(0), kcache.data_ptr(),
+                                     vcache.data_ptr(), kcache.shape[2], sites, heads, Tq, pos0), "sf_op_kv_append")
+
+
+def spatial_attention(qkv: torch.Tensor, frames: int, heads: int, S: int, scale: float,
+                      want_probs: bool = False):
+    _req(qkv)
+    D = heads * 64
+    out = torch.empty(frames * S, D, dtype=qkv.dtype, device=qkv.device)
+    probs = torch.empty(frames, heads, S, S, dtype=torch.float32, device=qkv.device) if want_probs else None
+    N.check(N.load().sf_op_spatial_attention(_stream(), sf_dtype(qkv.dtype), qkv.data_ptr(), qkv.stride(0),
+                                             out.data_ptr(), out.stride(0), frames, heads, S, scale, _p(probs)),
+            "sf_op_spatial_attention")
+    return (out, probs) if want_probs else out
+
+
+def pool_attention(kv: torch.Tensor, q: torch.Tensor, frames: int, heads: int, S: int) -> torch.Tensor:
+    _req(kv, q)
+    assert q.dtype == torch.float32
+    out = torch.empty(frames, heads * 64, dtype=kv.dtype, device=kv.device)
+    N.check(N.load().sf_op_pool_attention(_stream(), sf_dtype(kv.dtype), kv.data_ptr(), kv.stride(0), q.data_ptr(),
+                                          out.data_ptr(), out.stride(0), frames, heads, S), "sf_op_pool_attention")
+    return out
