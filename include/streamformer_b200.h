@@ -11,7 +11,7 @@
  *  - every function returns 0 on success or a negative sf_status; sf_last_error() returns a
  *    thread-local message describing the last failure;
  *  - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
- *    nothing synchronises the host and nothing allocates inside sf_forward*/sf_layer_forward;
+ *    nothing synchronises the host and nothing allocates inside the forward calls;
  *  - a context is bound to one device and is NOT thread-safe (same as the reference: one model
  *    replica per process / GPU);
  *  - activations are bf16 or fp16 (sf_config.dtype); residual stream rows are ordered (b, n, t)
