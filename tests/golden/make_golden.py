@@ -72,7 +72,8 @@ def oracle_cfg(case) -> O.OracleConfig:
 
 
 def load_into(model: torch.nn.Module, weights) -> None:
-    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
+    own = set(model.state_dict().keys())
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items() if k in own or not k.endswith(".mask")}
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected
     assert all("mask" in m for m in missing), missing
