@@ -76,6 +76,14 @@ const char* sf_version(void);
 /* kernels launched by this library since it was loaded */
 uint64_t sf_launch_count(void);
 
+/* In-situ profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.
+ * sf_profile_collect synchronises the device and returns, per kernel class (0 gemm, 1 layernorm,
+ * 2 im2col, 3 temporal attention, 4 spatial attention, 5 pooling attention, 6 kv append, 7 other),
+ * the summed duration [ms], executed FLOPs, algorithmic bytes and launch count since the last call. */
+#define SF_PROFILE_CLASSES 8
+int sf_profile(int enable);
+int sf_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int n_classes);
+
 /* ---- model lifetime ---------------------------------------------------------------------- */
 /* replaces TimesformerMultiTaskingModelSigLIP.__init__ (…siglip.py:1244-1258) */
 int sf_create(const sf_config* cfg, int device, sf_ctx** out);

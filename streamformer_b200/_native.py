@@ -19,7 +19,7 @@ SF_ROW_IDENTITY, SF_ROW_BTN_TO_BNT, SF_ROW_BNT_TO_BTN = 0, 1, 2
 
 # every symbol include/streamformer_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
-    "sf_last_error", "sf_version", "sf_launch_count",
+    "sf_last_error", "sf_version", "sf_launch_count", "sf_profile", "sf_profile_collect",
     "sf_create", "sf_destroy", "sf_bind_weights", "sf_set_pos_embed",
     "sf_workspace_bytes", "sf_forward",
     "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_forward_stream",
@@ -75,6 +75,9 @@ def load() -> C.CDLL:
     lib.sf_last_error.restype = C.c_char_p
     lib.sf_version.restype = C.c_char_p
     lib.sf_launch_count.restype = C.c_uint64
+    lib.sf_profile.argtypes = [i]
+    lib.sf_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_longlong), i]
     lib.sf_create.argtypes = [C.POINTER(SfConfig), i, C.POINTER(vp)]
     lib.sf_destroy.argtypes = [vp]
     lib.sf_bind_weights.argtypes = [vp, vp, C.POINTER(SfWeightDesc), i]
@@ -118,6 +121,22 @@ def launch_count() -> int:
 
 def version() -> str:
     return load().sf_version().decode()
+
+
+PROFILE_CLASSES = ["gemm", "layernorm", "im2col", "temporal_attention", "spatial_attention", "pool_attention",
+                   "kv_append", "other"]
+
+
+def profile(enable: bool) -> None:
+    load().sf_profile(1 if enable else 0)
+
+
+def profile_collect() -> dict:
+    n = len(PROFILE_CLASSES)
+    ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(load().sf_profile_collect(ms, fl, by, cnt, n), "sf_profile_collect")
+    return {PROFILE_CLASSES[k]: {"ms": ms[k], "flops": fl[k], "bytes": by[k], "launches": int(cnt[k])} for k in range(n)}
 
 
 def ptr_array(ptrs: Optional[Sequence[int]]):

@@ -466,6 +466,8 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
   a.tasks = static_cast<long>(sites) * heads * a.qtiles;
   a.scale_log2 = scale * kLog2e;
   const long blocks = (a.tasks + kTWarps - 1) / kTWarps;
+  ProfScope ps(stream, kProfTemporalAttn, 4.0 * sites * heads * static_cast<double>(Tq) * Tk * kHd,
+               2.0 * sites * heads * kHd * (2.0 * Tq + 2.0 * Tk));
   if (dtype == kBF16) temporal_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kTWarps * 32, 0, stream>>>(a);
   else temporal_attn_kernel<__half><<<static_cast<unsigned>(blocks), kTWarps * 32, 0, stream>>>(a);
   return check_launch("temporal_attention");
@@ -479,6 +481,7 @@ int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void*
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
   // bf16 and fp16 are both 2-byte payloads: one instantiation moves either
+  ProfScope ps(stream, kProfKvAppend, 0.0, 8.0 * sites * heads * static_cast<double>(Tq) * kHd);
   kv_append_kernel<__nv_bfloat16><<<static_cast<int>(blocks), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv, reinterpret_cast<__nv_bfloat16*>(kcache),
       reinterpret_cast<__nv_bfloat16*>(vcache), Tcap, sites, heads, Tq, pos0);
@@ -497,8 +500,12 @@ int spatial_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qk
   a.qblocks = (S + kSWarps * 16 - 1) / (kSWarps * 16);
   a.scale_log2 = scale * kLog2e;
   const long blocks = static_cast<long>(frames) * heads * a.qblocks;
-  if (dtype == kBF16) spatial_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kSWarps * 32, 0, stream>>>(a);
-  else spatial_attn_kernel<__half><<<static_cast<unsigned>(blocks), kSWarps * 32, 0, stream>>>(a);
+  {
+    ProfScope ps(stream, kProfSpatialAttn, 4.0 * frames * heads * static_cast<double>(S) * S * kHd,
+                 2.0 * frames * heads * kHd * 4.0 * S);
+    if (dtype == kBF16) spatial_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kSWarps * 32, 0, stream>>>(a);
+    else spatial_attn_kernel<__half><<<static_cast<unsigned>(blocks), kSWarps * 32, 0, stream>>>(a);
+  }
   int rc = check_launch("spatial_attention");
   if (rc || !probs) return rc;
   const long rows = static_cast<long>(frames) * heads * S;
@@ -517,6 +524,8 @@ int pool_attention(cudaStream_t stream, int dtype, const void* kv, int ld_kv, co
   if (dtype != kBF16 && dtype != kF16) { set_error("pool_attention: dtype must be bf16/f16"); return -1; }
   const long tasks = static_cast<long>(frames) * heads;
   const long blocks = (tasks + 3) / 4;
+  ProfScope ps(stream, kProfPoolAttn, 4.0 * frames * heads * static_cast<double>(S) * kHd,
+               2.0 * frames * heads * kHd * 2.0 * S);
   if (dtype == kBF16) pool_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(kv), ld_kv, q, reinterpret_cast<__nv_bfloat16*>(out), ld_out, frames, heads, S);
   else pool_attn_kernel<__half><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(

@@ -3,6 +3,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <vector>
 
 #include "sf_kernels.h"
 #include "sf_ptx.cuh"
@@ -22,6 +23,38 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 uint64_t launch_count() { return g_launches.load(); }
+
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_recs;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void prof_enable(bool on) { g_prof_on = on; }
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(cudaStream_t st, int cls, double flops, double bytes) {
+  ProfRec r; r.a = take_event(); r.b = take_event(); r.cls = cls; r.flops = flops; r.bytes = bytes;
+  cudaEventRecord(r.a, st);
+  g_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) { if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, st); }
+int prof_collect(double* ms, double* flops, double* bytes, long long* launches, int n) {
+  for (int i = 0; i < n; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { set_error("prof_collect: %s", cudaGetErrorString(e)); return -2; }
+  for (auto& r : g_recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (r.cls >= 0 && r.cls < n) { ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1; }
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
+  }
+  g_recs.clear();
+  return 0;
+}
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }
 
 namespace {

@@ -367,7 +367,12 @@ int launch_gemm(cudaStream_t stream, int dtype, const void* A, int lda, const vo
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tcgen05_kernel<T, BN><<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, p);
+  {
+    ProfScope ps(stream, kProfGemm, 2.0 * p.M * p.N * p.K,
+                 2.0 * (static_cast<double>(p.M) * p.K + static_cast<double>(p.N) * p.K +
+                        static_cast<double>(p.M) * p.N * (p.epi.residual ? 2 : 1)));
+    gemm_tcgen05_kernel<T, BN><<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, p);
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

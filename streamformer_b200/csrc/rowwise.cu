@@ -174,8 +174,11 @@ int launch_im2col(cudaStream_t st, const void* pix, void* out, int BT, int C, in
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 32) blocks = 148L * 32;
   if (blocks < 1) blocks = 1;
-  im2col_kernel<PixT, T><<<static_cast<int>(blocks), 256, 0, st>>>(
-      reinterpret_cast<const PixT*>(pix), reinterpret_cast<T*>(out), BT, C, H, W, P);
+  {
+    ProfScope ps(st, kProfIm2col, 0.0, static_cast<double>(total) * 8 * (sizeof(PixT) + sizeof(T)));
+    im2col_kernel<PixT, T><<<static_cast<int>(blocks), 256, 0, st>>>(
+        reinterpret_cast<const PixT*>(pix), reinterpret_cast<T*>(out), BT, C, H, W, P);
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("im2col launch: %s", cudaGetErrorString(e)); return -2; }
@@ -194,6 +197,7 @@ int layernorm(cudaStream_t stream, int dtype, const void* x, int ldx, const floa
   const int threads = 256, wpb = threads / 32;
   long blocks = (static_cast<long>(M) + wpb - 1) / wpb;
   if (blocks > 148L * 8 * 4) blocks = 148L * 8 * 4;
+  ProfScope ps(stream, kProfLayerNorm, 0.0, 4.0 * static_cast<double>(M) * D);
   if (dtype == kBF16) {
     layernorm_kernel<__nv_bfloat16><<<static_cast<int>(blocks), threads, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps,

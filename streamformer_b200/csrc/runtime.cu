@@ -441,6 +441,10 @@ extern "C" {
 const char* sf_last_error(void) { return last_error(); }
 const char* sf_version(void) { return "streamformer_b200 0.1 (sm_100a)"; }
 uint64_t sf_launch_count(void) { return launch_count(); }
+int sf_profile(int enable) { prof_enable(enable != 0); return 0; }
+int sf_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int n_classes) {
+  return prof_collect(ms, flops, bytes, launches, n_classes);
+}
 
 int sf_create(const sf_config* cfg, int device, sf_ctx** out) {
   if (!cfg || !out) { set_error("sf_create: null argument"); return SF_ERR_INVALID; }

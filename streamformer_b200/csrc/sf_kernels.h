@@ -86,6 +86,23 @@ int cast(cudaStream_t stream, int src_dtype, const void* src, int dst_dtype, voi
 uint64_t launch_count();
 void count_launch(int n = 1);
 
+// Optional in-situ profiling: when enabled every launcher brackets its kernel with CUDA events on
+// the launching stream; collect() synchronises and sums elapsed time per kernel class.
+enum ProfClass : int { kProfGemm = 0, kProfLayerNorm, kProfIm2col, kProfTemporalAttn, kProfSpatialAttn,
+                       kProfPoolAttn, kProfKvAppend, kProfOther, kProfNumClasses };
+void prof_enable(bool on);
+bool prof_enabled();
+void prof_begin(cudaStream_t st, int cls, double flops, double bytes);
+void prof_end(cudaStream_t st);
+int prof_collect(double* ms, double* flops, double* bytes, long long* launches, int n);
+struct ProfScope {
+  cudaStream_t st; bool on;
+  ProfScope(cudaStream_t s, int cls, double flops = 0.0, double bytes = 0.0) : st(s), on(prof_enabled()) {
+    if (on) prof_begin(st, cls, flops, bytes);
+  }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+
 const char* last_error();
 void set_error(const char* fmt, ...);
 

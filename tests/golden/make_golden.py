@@ -105,7 +105,7 @@ def run_case(name: str) -> None:
         out["attention_0_sub"] = np.ascontiguousarray(r.attentions[0].numpy()[::3, ::5, ::13, :])
     else:
         mod = import_twin()
-        cfg = mod.TimesformerConfig(num_hidden_layers=case["layers"], enable_causal_temporal=case["causal"],
+        cfg = mod.StreamformerConfig(num_hidden_layers=case["layers"], enable_causal_temporal=case["causal"],
                                     num_frames=ocfg.num_frames)
         model = mod.TimesformerMultiTaskingModelSigLIP(cfg).eval()
         load_into(model, weights)
