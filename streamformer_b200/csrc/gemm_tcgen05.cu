@@ -40,7 +40,9 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kEpiOffset = kBarOffset + 256;                 // after the barriers
+  static constexpr int kEpiBytesPerWarp = 2048 + 512;                 // 32x64 B staging + 128-float bias slice
+  static constexpr int kTotal = kEpiOffset + kEpiWarps * kEpiBytesPerWarp + 1024;  // + alignment slack
 };
 
 template <typename T> struct UmmaFmt;
@@ -170,14 +172,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter) x kColsPerWarp columns and walks
+    // them in 32-column chunks:  tcgen05.ld -> bias/act/embed/residual in the thread==row layout ->
+    // 2 KB swizzled smem staging -> 16-byte global stores in a (8 rows x 64 B) coalesced layout.
+    // Residual rows travel the same staging buffer in the opposite direction first.
     const int ew = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;              // which half of the BN columns
-    constexpr int kColsPerWarp = BN / 2;
+    const int colgrp = ew >> 2;            // which slice of the BN columns
+    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+    uint8_t* stage_buf = smem + L::kEpiOffset + ew * L::kEpiBytesPerWarp;
+    float* bias_s = reinterpret_cast<float*>(stage_buf + 2048);
+    const uint32_t stage_u = smem_u32(stage_buf);
     const GemmEpilogue& e = p.epi;
     const float gscale = e.gate ? tanhf(__ldg(e.gate)) : 1.0f;
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(e.residual);
+    const int crow0 = lane >> 2, cchunk = lane & 3;   // coalesced layout: rows crow0 + 8*i, 16-byte chunk cchunk
+    auto stage_addr = [&](int row, int ch) -> uint32_t {
+      return stage_u + static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -209,72 +222,106 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           e.time_emb ? e.time_emb + static_cast<long>(time_index(e.time_off + frame, e.time_len,
                                                                 e.time_total)) * p.N
                      : nullptr;
+      // output rows handled by this lane in the coalesced layout (-1 = out of range)
+      const int r_own = row_ok ? static_cast<int>(r) : -1;
+      int r_c[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r_c[i] = __shfl_sync(0xffffffffu, r_own, crow0 + 8 * i);
+      const int wcol0 = n0 + colgrp * kColsPerWarp;
+      // this warp's bias slice -> smem (overlaps the MMAs of this tile)
+      if (e.bias) {
+#pragma unroll
+        for (int j = lane; j < kColsPerWarp; j += 32) bias_s[j] = (wcol0 + j < p.N) ? __ldg(e.bias + wcol0 + j) : 0.f;
+      }
+      __syncwarp();
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
-                              half * kColsPerWarp;
+                              colgrp * kColsPerWarp;
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(t_base + c * 32, raw);
-        tmem_ld_wait();
-        const int col0 = n0 + half * kColsPerWarp + c * 32;
-        if (row_ok && col0 < p.N) {
-          float v[32];
+        const int col0 = wcol0 + c * 32;
+        const int ccol = col0 + cchunk * 8;
+        const bool ccol_ok = ccol < p.N;
+        uint4 rr[4];
+        if (res) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns = one 16-byte store each
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              float* vv = v + g * 8;
-              if (e.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
-                vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-                vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-              }
-              if (e.act == kActGeluErf) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
-              } else if (e.act == kActGeluTanh) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
-              }
-              if (pos_row) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + col + 4));
-                vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-                vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-              }
-              if (time_row) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(time_row + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(time_row + col + 4));
-                vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-                vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-              }
-              if (res) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res + r * e.ldr + col);
-                const float2 r0 = Pack2<T>::unpack(rr.x), r1 = Pack2<T>::unpack(rr.y);
-                const float2 r2 = Pack2<T>::unpack(rr.z), r3 = Pack2<T>::unpack(rr.w);
-                vv[0] = r0.x + gscale * vv[0]; vv[1] = r0.y + gscale * vv[1];
-                vv[2] = r1.x + gscale * vv[2]; vv[3] = r1.y + gscale * vv[3];
-                vv[4] = r2.x + gscale * vv[4]; vv[5] = r2.y + gscale * vv[5];
-                vv[6] = r3.x + gscale * vv[6]; vv[7] = r3.y + gscale * vv[7];
-              } else if (e.gate) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] *= gscale;
-              }
-              uint4 o;
-              o.x = Pack2<T>::pack(vv[0], vv[1]);
-              o.y = Pack2<T>::pack(vv[2], vv[3]);
-              o.z = Pack2<T>::pack(vv[4], vv[5]);
-              o.w = Pack2<T>::pack(vv[6], vv[7]);
-              *reinterpret_cast<uint4*>(out + r * p.ldo + col) = o;
-            }
+          for (int i = 0; i < 4; ++i) {
+            rr[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (r_c[i] >= 0 && ccol_ok)
+              rr[i] = *reinterpret_cast<const uint4*>(res + static_cast<long>(r_c[i]) * e.ldr + ccol);
           }
         }
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(t_base + c * 32, raw);
+        if (res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(crow0 + 8 * i, cchunk)),
+                         "r"(rr[i].x), "r"(rr[i].y), "r"(rr[i].z), "r"(rr[i].w) : "memory");
+          }
+          __syncwarp();
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns
+          float vv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vv[j] = __uint_as_float(raw[g * 8 + j]);
+          const int col = col0 + g * 8;
+          if (e.bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c * 32 + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c * 32 + g * 8 + 4);
+            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+          }
+          if (e.act == kActGeluErf) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
+          } else if (e.act == kActGeluTanh) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
+          }
+          if (pos_row && row_ok && col < p.N) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + col + 4));
+            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+          }
+          if (time_row && row_ok && col < p.N) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(time_row + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(time_row + col + 4));
+            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+          }
+          const uint32_t my = stage_addr(lane, g);
+          if (res) {
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(my));
+            const float2 r0 = Pack2<T>::unpack(q.x), r1 = Pack2<T>::unpack(q.y);
+            const float2 r2 = Pack2<T>::unpack(q.z), r3 = Pack2<T>::unpack(q.w);
+            vv[0] = r0.x + gscale * vv[0]; vv[1] = r0.y + gscale * vv[1];
+            vv[2] = r1.x + gscale * vv[2]; vv[3] = r1.y + gscale * vv[3];
+            vv[4] = r2.x + gscale * vv[4]; vv[5] = r2.y + gscale * vv[5];
+            vv[6] = r3.x + gscale * vv[6]; vv[7] = r3.y + gscale * vv[7];
+          } else if (e.gate) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] *= gscale;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my), "r"(Pack2<T>::pack(vv[0], vv[1])),
+                       "r"(Pack2<T>::pack(vv[2], vv[3])), "r"(Pack2<T>::pack(vv[4], vv[5])),
+                       "r"(Pack2<T>::pack(vv[6], vv[7])) : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 q;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                       : "r"(stage_addr(crow0 + 8 * i, cchunk)));
+          if (r_c[i] >= 0 && ccol_ok) *reinterpret_cast<uint4*>(out + static_cast<long>(r_c[i]) * p.ldo + ccol) = q;
+        }
+        __syncwarp();  // staging buffer is reused by the next chunk
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();

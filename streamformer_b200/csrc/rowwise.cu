@@ -11,100 +11,131 @@
 namespace sf {
 namespace {
 
-constexpr int kLnMaxChunks = 4;  // register-cached path covers D <= 8*32*4 = 1024
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = Pack2<T>::unpack(u.x), b = Pack2<T>::unpack(u.y);
+  const float2 c = Pack2<T>::unpack(u.z), d = Pack2<T>::unpack(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+__device__ __forceinline__ long map_row(long m, int row_map, int Tn, int Sn) {
+  if (row_map == kRowBNTtoBTN) {
+    const long t = m % Tn, bn = m / Tn;
+    const long n = bn % Sn, b = bn / Sn;
+    return (b * Tn + t) * Sn + n;
+  }
+  if (row_map == kRowBTNtoBNT) {
+    const long n = m % Sn, bt = m / Sn;
+    const long t = bt % Tn, b = bt / Tn;
+    return (b * Sn + n) * Tn + t;
+  }
+  return m;
+}
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ uint4 normalize8(const float (&v)[8], float mean, float rstd, const float* gamma,
+                                            const float* beta) {
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma));
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + 4));
+  uint4 o;
+  o.x = Pack2<T>::pack((v[0] - mean) * rstd * g0.x + b0.x, (v[1] - mean) * rstd * g0.y + b0.y);
+  o.y = Pack2<T>::pack((v[2] - mean) * rstd * g0.z + b0.z, (v[3] - mean) * rstd * g0.w + b0.w);
+  o.z = Pack2<T>::pack((v[4] - mean) * rstd * g1.x + b1.x, (v[5] - mean) * rstd * g1.y + b1.y);
+  o.w = Pack2<T>::pack((v[6] - mean) * rstd * g1.z + b1.z, (v[7] - mean) * rstd * g1.w + b1.w);
+  return o;
+}
+
+// One warp per row, the whole row cached in registers: NCH 16-byte chunks per lane (D <= NCH*256).
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256, 5)
 layernorm_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, T* __restrict__ y, int ldy, int M, int D,
                  int row_map, int Tn, int Sn) {
-  const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nchunks = D >> 3;  // 8 elements (16 bytes) per chunk
-  for (long m = static_cast<long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); m < M;
-       m += static_cast<long>(gridDim.x) * warps_per_block) {
-    const T* xr = x + m * ldx;
-    float v[kLnMaxChunks][8];
-    float sum = 0.f;
+  const int nchunks = D >> 3;
+  const long m = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const T* xr = x + m * ldx;
+  float v[NCH][8];
+  float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxChunks; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) {
-        const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
-        const float2 a = Pack2<T>::unpack(u.x), b = Pack2<T>::unpack(u.y);
-        const float2 cc = Pack2<T>::unpack(u.z), d = Pack2<T>::unpack(u.w);
-        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
-        v[i][4] = cc.x; v[i][5] = cc.y; v[i][6] = d.x; v[i][7] = d.y;
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      unpack8<T>(*reinterpret_cast<const uint4*>(xr + c * 8), v[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += v[i][j];
-      }
-    }
-    // chunks beyond the register cache (D > 1024): re-read
-    for (int c = lane + 32 * kLnMaxChunks; c < nchunks; c += 32) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
-      const float2 a = Pack2<T>::unpack(u.x), b = Pack2<T>::unpack(u.y);
-      const float2 cc = Pack2<T>::unpack(u.z), d = Pack2<T>::unpack(u.w);
-      sum += a.x + a.y + b.x + b.y + cc.x + cc.y + d.x + d.y;
-    }
-    const float mean = warp_sum(sum) / static_cast<float>(D);
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxChunks; ++i) {
-      if (lane + 32 * i < nchunks) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[i][j] - mean;
-          sq += d * d;
-        }
-      }
-    }
-    for (int c = lane + 32 * kLnMaxChunks; c < nchunks; c += 32) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = Pack2<T>::unpack(w[j]);
-        sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
-
-    long r = m;
-    if (row_map == kRowBNTtoBTN) {
-      const long t = m % Tn, bn = m / Tn;
-      const long n = bn % Sn, b = bn / Sn;
-      r = (b * Tn + t) * Sn + n;
-    } else if (row_map == kRowBTNtoBNT) {
-      const long n = m % Sn, bt = m / Sn;
-      const long t = bt % Tn, b = bt / Tn;
-      r = (b * Sn + n) * Tn + t;
-    }
-    T* yr = y + r * ldy;
-    auto emit = [&](int c, const float (&vals)[8]) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c * 8 + 4));
-      uint4 o;
-      o.x = Pack2<T>::pack((vals[0] - mean) * rstd * g0.x + b0.x, (vals[1] - mean) * rstd * g0.y + b0.y);
-      o.y = Pack2<T>::pack((vals[2] - mean) * rstd * g0.z + b0.z, (vals[3] - mean) * rstd * g0.w + b0.w);
-      o.z = Pack2<T>::pack((vals[4] - mean) * rstd * g1.x + b1.x, (vals[5] - mean) * rstd * g1.y + b1.y);
-      o.w = Pack2<T>::pack((vals[6] - mean) * rstd * g1.z + b1.z, (vals[7] - mean) * rstd * g1.w + b1.w);
-      *reinterpret_cast<uint4*>(yr + c * 8) = o;
-    };
-#pragma unroll
-    for (int i = 0; i < kLnMaxChunks; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunks) emit(c, v[i]);
-    }
-    for (int c = lane + 32 * kLnMaxChunks; c < nchunks; c += 32) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
-      const float2 a = Pack2<T>::unpack(u.x), b = Pack2<T>::unpack(u.y);
-      const float2 cc = Pack2<T>::unpack(u.z), d = Pack2<T>::unpack(u.w);
-      const float vals[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
-      emit(c, vals);
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
     }
   }
+  const float mean = warp_sum(sum) / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    if (lane + 32 * i < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
+  T* yr = y + map_row(m, row_map, Tn, Sn) * ldy;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks)
+      *reinterpret_cast<uint4*>(yr + c * 8) = normalize8<T>(v[i], mean, rstd, gamma + c * 8, beta + c * 8);
+  }
+}
+
+// Any D (multiple of 8): three passes over the row through L1/L2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_wide_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, T* __restrict__ y, int ldy, int M, int D,
+                      int row_map, int Tn, int Sn) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = D >> 3;
+  const long m = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const T* xr = x + m * ldx;
+  float f[8];
+  float sum = 0.f;
+  for (int c = lane; c < nchunks; c += 32) {
+    unpack8<T>(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += f[j];
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(D);
+  float sq = 0.f;
+  for (int c = lane; c < nchunks; c += 32) {
+    unpack8<T>(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sq += (f[j] - mean) * (f[j] - mean);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
+  T* yr = y + map_row(m, row_map, Tn, Sn) * ldy;
+  for (int c = lane; c < nchunks; c += 32) {
+    unpack8<T>(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+    *reinterpret_cast<uint4*>(yr + c * 8) = normalize8<T>(f, mean, rstd, gamma + c * 8, beta + c * 8);
+  }
+}
+
+template <typename T>
+void launch_layernorm(cudaStream_t stream, const void* x, int ldx, const float* gamma, const float* beta, float eps,
+                      void* y, int ldy, int M, int D, int row_map, int Tn, int Sn) {
+  const int threads = 256, wpb = threads / 32;
+  const unsigned blocks = static_cast<unsigned>((static_cast<long>(M) + wpb - 1) / wpb);
+  const T* xi = reinterpret_cast<const T*>(x);
+  T* yo = reinterpret_cast<T*>(y);
+  if (D <= 256) layernorm_kernel<T, 1><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
+  else if (D <= 512) layernorm_kernel<T, 2><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
+  else if (D <= 768) layernorm_kernel<T, 3><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
+  else if (D <= 1024) layernorm_kernel<T, 4><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
+  else layernorm_wide_kernel<T><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
 }
 
 template <typename PixT>
@@ -194,18 +225,11 @@ int layernorm(cudaStream_t stream, int dtype, const void* x, int ldx, const floa
     set_error("layernorm: D, ldx, ldy must be multiples of 8 (D=%d ldx=%d ldy=%d)", D, ldx, ldy);
     return -1;
   }
-  const int threads = 256, wpb = threads / 32;
-  long blocks = (static_cast<long>(M) + wpb - 1) / wpb;
-  if (blocks > 148L * 8 * 4) blocks = 148L * 8 * 4;
   ProfScope ps(stream, kProfLayerNorm, 0.0, 4.0 * static_cast<double>(M) * D);
   if (dtype == kBF16) {
-    layernorm_kernel<__nv_bfloat16><<<static_cast<int>(blocks), threads, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps,
-        reinterpret_cast<__nv_bfloat16*>(y), ldy, M, D, row_map, T, S);
+    launch_layernorm<__nv_bfloat16>(stream, x, ldx, gamma, beta, eps, y, ldy, M, D, row_map, T, S);
   } else if (dtype == kF16) {
-    layernorm_kernel<__half><<<static_cast<int>(blocks), threads, 0, stream>>>(
-        reinterpret_cast<const __half*>(x), ldx, gamma, beta, eps, reinterpret_cast<__half*>(y), ldy,
-        M, D, row_map, T, S);
+    launch_layernorm<__half>(stream, x, ldx, gamma, beta, eps, y, ldy, M, D, row_map, T, S);
   } else {
     set_error("layernorm: dtype must be bf16 or f16");
     return -1;
