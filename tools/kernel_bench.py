@@ -13,7 +13,12 @@ from streamformer_b200 import ops  # noqa: E402
 from streamformer_b200 import _native as N  # noqa: E402
 
 
-def timeit(fn, nrot, reps=20, warm=3):
+REPS, WARM = 20, 3
+
+
+def timeit(fn, nrot, reps=None, warm=None):
+    reps = REPS if reps is None else reps
+    warm = WARM if warm is None else warm
     for i in range(warm):
         fn(i % nrot)
     torch.cuda.synchronize()
@@ -31,7 +36,11 @@ def main():
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--T", type=int, default=16)
     ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--warm", type=int, default=3)
     a = ap.parse_args()
+    global REPS, WARM
+    REPS, WARM = a.reps, a.warm
     dev, dt = "cuda", torch.bfloat16
     S, D, I = 196, 768, 3072
     M = a.B * a.T * S
