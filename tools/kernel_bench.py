@@ -78,6 +78,20 @@ def main():
         gemm_case("fc2 (bias+res)", D, I, residual=True)
         gemm_case("head kv (bias)", 2 * D, D)
 
+    if a.only and "cublas" in a.only:
+        # library reference on the same shapes (context only: cuBLAS is not on the product path)
+        for name, Nn, K in (("qkv", 3 * D, D), ("proj", D, D), ("fc1", I, D), ("fc2", D, I)):
+            As = [torch.randn(M, K, device=dev, dtype=dt) for _ in range(nrot)]
+            Ws = [torch.randn(Nn, K, device=dev, dtype=dt) * 0.05 for _ in range(nrot)]
+            outs = [torch.empty(M, Nn, device=dev, dtype=dt) for _ in range(nrot)]
+            bias = torch.randn(Nn, device=dev, dtype=dt)
+            ms = timeit(lambda i: torch.matmul(As[i], Ws[i].t(), out=outs[i]), nrot)
+            tf = 2.0 * M * Nn * K / (ms * 1e-3) / 1e12
+            ms2 = timeit(lambda i: torch.addmm(bias, As[i], Ws[i].t(), out=outs[i]), nrot)
+            tf2 = 2.0 * M * Nn * K / (ms2 * 1e-3) / 1e12
+            res["cublas " + name] = {"ms": round(ms, 4), "tflops": round(tf, 1), "addmm_tflops": round(tf2, 1)}
+            print(f"cuBLAS {name:8s} M={M} N={Nn} K={K}: {ms*1e3:8.1f} us {tf:7.1f} TFLOP/s | addmm(bias) {ms2*1e3:8.1f} us {tf2:7.1f}", flush=True)
+
     if not a.only or "ln" in a.only:
         xs = [torch.randn(M, D, device=dev, dtype=dt) for _ in range(nrot)]
         gmm, bta = torch.randn(D, device=dev), torch.randn(D, device=dev)
