@@ -15,7 +15,9 @@
  *  - a context is bound to one device and is NOT thread-safe (same as the reference: one model
  *    replica per process / GPU);
  *  - activations are bf16 or fp16 (sf_config.dtype); residual stream rows are ordered (b, n, t)
- *    exactly like the reference's hidden_states [B, N*T, D] (…siglip.py:452-454).
+ *    exactly like the reference's hidden_states [B, N*T, D] (…siglip.py:452-454), and stay in that
+ *    order through every kernel of a layer (the spatial attention reads its frame with a row stride
+ *    of T instead of the reference's permute copies, …siglip.py:962-991).
  */
 #ifndef STREAMFORMER_B200_H_
 #define STREAMFORMER_B200_H_
@@ -147,6 +149,14 @@ typedef struct sf_gemm_epilogue {
   const void* residual; int ldr; const float* gate;
   int row_map; int T; int S;
   const float* pos; const float* time_emb; int time_len; int time_total; int time_off;
+  /* LayerNorm folded into the GEMM (nn.LayerNorm + nn.Linear pairs, …siglip.py:943+578, 974+691, 997+820):
+   * A holds the raw rows, W is pre-scaled by gamma, bias = b + W.beta, and
+   *   out = rstd[m] * (A.W^T - mean[m] * ln_colsum[n]) + bias[n]
+   * with mean/rstd from ln_parts partial (sum, sumsq) float pairs per row: ln_stats[part][M][2]. */
+  const void* ln_stats; int ln_parts; const float* ln_colsum; float ln_eps;
+  /* optional by-product of the residual / embed epilogues: partial (sum, sumsq) of every output row,
+   * [sf_op_gemm_stats_parts(M, N)][M][2] floats, in the layout ln_stats consumes */
+  void* stats_out;
 } sf_gemm_epilogue;
 int sf_op_gemm(void* stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out,
                int ldo, int M, int N, int K, const sf_gemm_epilogue* epi);
@@ -160,8 +170,13 @@ int sf_op_temporal_attention(void* stream, int dtype, const void* qkv, int ld_qk
                              int Tq, int Tk, int q_off, int causal, float scale);
 int sf_op_kv_append(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
                     int Tcap, int sites, int heads, int Tq, int pos0);
+/* T_inner <= 1: token n of frame f at row f*S + n; T_inner > 1: at row (b*S + n)*T_inner + t with
+ * f = b*T_inner + t (the residual stream's (b,n,t) order, read in place) */
 int sf_op_spatial_attention(void* stream, int dtype, const void* qkv, int ld_qkv, void* out, int ld_out,
-                            int frames, int heads, int S, float scale, float* probs);
+                            int frames, int heads, int S, int T_inner, float scale, float* probs);
+/* stats[m] = (sum_d x[m,d], sum_d x[m,d]^2): the one-partial table a folded LayerNorm consumes */
+int sf_op_rowstats(void* stream, int dtype, const void* x, int ldx, int M, int D, void* stats);
+int sf_op_gemm_stats_parts(int M, int N);
 int sf_op_pool_attention(void* stream, int dtype, const void* kv, int ld_kv, const float* q, void* out,
                          int ld_out, int frames, int heads, int S);
 

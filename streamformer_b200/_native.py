@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_forward_stream",
     "sf_embed_forward", "sf_layer_forward", "sf_final_norm", "sf_head_forward",
     "sf_op_gemm", "sf_op_layernorm", "sf_op_im2col", "sf_op_temporal_attention", "sf_op_kv_append",
-    "sf_op_spatial_attention", "sf_op_pool_attention",
+    "sf_op_spatial_attention", "sf_op_pool_attention", "sf_op_rowstats", "sf_op_gemm_stats_parts",
 ]
 
 
@@ -54,6 +54,8 @@ class SfGemmEpilogue(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int), ("residual", C.c_void_p), ("ldr", C.c_int), ("gate", C.c_void_p),
         ("row_map", C.c_int), ("T", C.c_int), ("S", C.c_int), ("pos", C.c_void_p), ("time_emb", C.c_void_p),
         ("time_len", C.c_int), ("time_total", C.c_int), ("time_off", C.c_int),
+        ("ln_stats", C.c_void_p), ("ln_parts", C.c_int), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -99,7 +101,9 @@ def load() -> C.CDLL:
     lib.sf_op_im2col.argtypes = [vp, i, vp, i, vp, i, i, i, i, i]
     lib.sf_op_temporal_attention.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, i, i, f]
     lib.sf_op_kv_append.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i, i]
-    lib.sf_op_spatial_attention.argtypes = [vp, i, vp, i, vp, i, i, i, i, f, vp]
+    lib.sf_op_spatial_attention.argtypes = [vp, i, vp, i, vp, i, i, i, i, i, f, vp]
+    lib.sf_op_rowstats.argtypes = [vp, i, vp, i, i, i, vp]
+    lib.sf_op_gemm_stats_parts.argtypes = [i, i]
     lib.sf_op_pool_attention.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)

@@ -137,6 +137,8 @@ template <typename T>
 __global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const TemporalArgs a) {
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   __shared__ __align__(128) uint8_t smem[kTWarps][2][16 * 128];  // per warp: K tile, V tile
+  griddep_wait();
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, c = lane & 3;
   const long task = static_cast<long>(blockIdx.x) * kTWarps + warp;
@@ -214,6 +216,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 kv_append_kernel(const T* __restrict__ qkv, long ld, T* __restrict__ kc, T* __restrict__ vc, int Tcap,
                  int sites, int heads, int Tq, int pos0) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int D = heads * kHd;
   const long total = static_cast<long>(sites) * Tq * heads * 8;  // 16-byte chunks per K (and per V)
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -239,11 +243,14 @@ struct SpatialArgs {
   const void* qkv; long ld;
   void* out; long out_ld;
   int frames, heads, S, qblocks;
+  int T_inner;   // <= 1: frame rows contiguous; > 1: frame (b,t) lives at rows (b*S + n)*T_inner + t
   float scale_log2;
 };
 
 template <typename T>
 __global__ void __launch_bounds__(kSWarps * 32) spatial_attn_kernel(const SpatialArgs a) {
+  griddep_wait();
+  griddep_launch_dependents();
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   __shared__ __align__(128) uint8_t smem[2][2][kSKeys * 128];  // [stage][K|V]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,8 +261,15 @@ __global__ void __launch_bounds__(kSWarps * 32) spatial_attn_kernel(const Spatia
   bid /= a.qblocks;
   const int h = bid % a.heads;
   const long frame = bid / a.heads;
+  // first row of the frame and distance (in rows) between its consecutive tokens
+  long row0 = frame * a.S, rstep = 1;
+  if (a.T_inner > 1) {
+    row0 = (frame / a.T_inner) * a.S * a.T_inner + frame % a.T_inner;
+    rstep = a.T_inner;
+  }
+  const long ld = a.ld * rstep, old = a.out_ld * rstep;
 
-  const T* base = reinterpret_cast<const T*>(a.qkv) + frame * a.S * a.ld + h * kHd;
+  const T* base = reinterpret_cast<const T*>(a.qkv) + row0 * a.ld + h * kHd;
   const T* kbase = base + D;
   const T* vbase = base + 2 * D;
   const int i0 = qb * (kSWarps * 16) + warp * 16;
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(kSWarps * 32) spatial_attn_kernel(const Spatia
   const bool ok0 = (i0 + g) < a.S, ok1 = (i0 + g + 8) < a.S;
 
   uint32_t qa[4][4];
-  load_q_frags<T>(qa, base + static_cast<long>(i0 + g) * a.ld, base + static_cast<long>(i0 + g + 8) * a.ld,
+  load_q_frags<T>(qa, base + static_cast<long>(i0 + g) * ld, base + static_cast<long>(i0 + g + 8) * ld,
                   ok0, ok1, c);
 
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(kSWarps * 32) spatial_attn_kernel(const Spatia
       const int idx = threadIdx.x + i * (kSWarps * 32);
       const int row = idx >> 3, ch = idx & 7;
       const bool ok = (kb0 + row) < a.S;
-      const long roff = static_cast<long>(ok ? kb0 + row : 0) * a.ld + ch * 8;
+      const long roff = static_cast<long>(ok ? kb0 + row : 0) * ld + ch * 8;
       cp_async_16(smem[stage][0] + tile_off(row, ch), kbase + roff, ok);
       cp_async_16(smem[stage][1] + tile_off(row, ch), vbase + roff, ok);
     }
@@ -324,17 +338,19 @@ __global__ void __launch_bounds__(kSWarps * 32) spatial_attn_kernel(const Spatia
     __syncthreads();
   }
   if (warp_active) {
-    T* obase = reinterpret_cast<T*>(a.out) + frame * a.S * a.out_ld + h * kHd;
-    finalize_store<T>(o, l_run, obase + static_cast<long>(i0 + g) * a.out_ld,
-                      obase + static_cast<long>(i0 + g + 8) * a.out_ld, ok0, ok1, c);
+    T* obase = reinterpret_cast<T*>(a.out) + row0 * a.out_ld + h * kHd;
+    finalize_store<T>(o, l_run, obase + static_cast<long>(i0 + g) * old,
+                      obase + static_cast<long>(i0 + g + 8) * old, ok0, ok1, c);
   }
 }
 
 // Debug path (output_attentions=True): normalised probabilities, one warp per query row.
 template <typename T>
 __global__ void __launch_bounds__(128)
-spatial_probs_kernel(const T* __restrict__ qkv, long ld, float* __restrict__ probs, int frames, int heads,
-                     int S, float scale) {
+spatial_probs_kernel(const T* __restrict__ qkv, long ld_in, float* __restrict__ probs, int frames, int heads,
+                     int S, int T_inner, float scale) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long row_id = static_cast<long>(blockIdx.x) * 4 + warp;  // (frame, head, query)
   const long total = static_cast<long>(frames) * heads * S;
@@ -343,7 +359,13 @@ spatial_probs_kernel(const T* __restrict__ qkv, long ld, float* __restrict__ pro
   const int h = static_cast<int>((row_id / S) % heads);
   const long frame = row_id / (static_cast<long>(S) * heads);
   const int D = heads * kHd;
-  const T* base = qkv + frame * S * ld + h * kHd;
+  long row0 = frame * S, rstep = 1;
+  if (T_inner > 1) {
+    row0 = (frame / T_inner) * S * T_inner + frame % T_inner;
+    rstep = T_inner;
+  }
+  const long ld = ld_in * rstep;
+  const T* base = qkv + row0 * ld_in + h * kHd;
   const T* q = base + static_cast<long>(qi) * ld;
   float* prow = probs + row_id * S;
   float qf[2];
@@ -378,6 +400,8 @@ __global__ void __launch_bounds__(128)
 pool_attn_kernel(const T* __restrict__ kv, long ld, const float* __restrict__ q, T* __restrict__ out,
                  long out_ld, int frames, int heads, int S) {
   __shared__ float sc[4][kPoolMaxS];
+  griddep_wait();
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long task = static_cast<long>(blockIdx.x) * 4 + warp;
   if (task >= static_cast<long>(frames) * heads) return;
@@ -468,8 +492,9 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
   const long blocks = (a.tasks + kTWarps - 1) / kTWarps;
   ProfScope ps(stream, kProfTemporalAttn, 4.0 * sites * heads * static_cast<double>(Tq) * Tk * kHd,
                2.0 * sites * heads * kHd * (2.0 * Tq + 2.0 * Tk));
-  if (dtype == kBF16) temporal_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kTWarps * 32, 0, stream>>>(a);
-  else temporal_attn_kernel<__half><<<static_cast<unsigned>(blocks), kTWarps * 32, 0, stream>>>(a);
+  LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(kTWarps * 32), 0, stream);
+  if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, temporal_attn_kernel<__nv_bfloat16>, a);
+  else cudaLaunchKernelEx(&lc.cfg, temporal_attn_kernel<__half>, a);
   return check_launch("temporal_attention");
 }
 
@@ -482,38 +507,42 @@ int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void*
   if (blocks > 148L * 16) blocks = 148L * 16;
   // bf16 and fp16 are both 2-byte payloads: one instantiation moves either
   ProfScope ps(stream, kProfKvAppend, 0.0, 8.0 * sites * heads * static_cast<double>(Tq) * kHd);
-  kv_append_kernel<__nv_bfloat16><<<static_cast<int>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv, reinterpret_cast<__nv_bfloat16*>(kcache),
-      reinterpret_cast<__nv_bfloat16*>(vcache), Tcap, sites, heads, Tq, pos0);
+  LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream);
+  cudaLaunchKernelEx(&lc.cfg, kv_append_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                     static_cast<long>(ld_qkv), reinterpret_cast<__nv_bfloat16*>(kcache),
+                     reinterpret_cast<__nv_bfloat16*>(vcache), Tcap, sites, heads, Tq, pos0);
   (void)dtype;
   return check_launch("kv_append");
 }
 
 int spatial_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* out, int ld_out,
-                      int frames, int heads, int S, float scale, float* probs) {
+                      int frames, int heads, int S, int T_inner, float scale, float* probs) {
   if (frames <= 0 || S <= 0) return 0;
   if (dtype != kBF16 && dtype != kF16) { set_error("spatial_attention: dtype must be bf16/f16"); return -1; }
   if ((ld_qkv % 8) || (ld_out % 2)) { set_error("spatial_attention: bad leading dims"); return -1; }
   SpatialArgs a;
   a.qkv = qkv; a.ld = ld_qkv; a.out = out; a.out_ld = ld_out;
-  a.frames = frames; a.heads = heads; a.S = S;
+  a.frames = frames; a.heads = heads; a.S = S; a.T_inner = T_inner;
+  if (T_inner > 1 && frames % T_inner) { set_error("spatial_attention: frames=%d is not a multiple of T_inner=%d", frames, T_inner); return -1; }
   a.qblocks = (S + kSWarps * 16 - 1) / (kSWarps * 16);
   a.scale_log2 = scale * kLog2e;
   const long blocks = static_cast<long>(frames) * heads * a.qblocks;
   {
     ProfScope ps(stream, kProfSpatialAttn, 4.0 * frames * heads * static_cast<double>(S) * S * kHd,
                  2.0 * frames * heads * kHd * 4.0 * S);
-    if (dtype == kBF16) spatial_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kSWarps * 32, 0, stream>>>(a);
-    else spatial_attn_kernel<__half><<<static_cast<unsigned>(blocks), kSWarps * 32, 0, stream>>>(a);
+    LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(kSWarps * 32), 0, stream);
+    if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, spatial_attn_kernel<__nv_bfloat16>, a);
+    else cudaLaunchKernelEx(&lc.cfg, spatial_attn_kernel<__half>, a);
   }
   int rc = check_launch("spatial_attention");
   if (rc || !probs) return rc;
   const long rows = static_cast<long>(frames) * heads * S;
   const long pb = (rows + 3) / 4;
-  if (dtype == kBF16) spatial_probs_kernel<__nv_bfloat16><<<static_cast<unsigned>(pb), 128, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv, probs, frames, heads, S, scale);
-  else spatial_probs_kernel<__half><<<static_cast<unsigned>(pb), 128, 0, stream>>>(
-      reinterpret_cast<const __half*>(qkv), ld_qkv, probs, frames, heads, S, scale);
+  LaunchCfg lp(dim3(static_cast<unsigned>(pb)), dim3(128), 0, stream);
+  if (dtype == kBF16) cudaLaunchKernelEx(&lp.cfg, spatial_probs_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                         static_cast<long>(ld_qkv), probs, frames, heads, S, T_inner, scale);
+  else cudaLaunchKernelEx(&lp.cfg, spatial_probs_kernel<__half>, reinterpret_cast<const __half*>(qkv),
+                          static_cast<long>(ld_qkv), probs, frames, heads, S, T_inner, scale);
   return check_launch("spatial_probs");
 }
 
@@ -526,10 +555,12 @@ int pool_attention(cudaStream_t stream, int dtype, const void* kv, int ld_kv, co
   const long blocks = (tasks + 3) / 4;
   ProfScope ps(stream, kProfPoolAttn, 4.0 * frames * heads * static_cast<double>(S) * kHd,
                2.0 * frames * heads * kHd * 2.0 * S);
-  if (dtype == kBF16) pool_attn_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(kv), ld_kv, q, reinterpret_cast<__nv_bfloat16*>(out), ld_out, frames, heads, S);
-  else pool_attn_kernel<__half><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
-      reinterpret_cast<const __half*>(kv), ld_kv, q, reinterpret_cast<__half*>(out), ld_out, frames, heads, S);
+  LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(128), 0, stream);
+  if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, pool_attn_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(kv),
+                                         static_cast<long>(ld_kv), q, reinterpret_cast<__nv_bfloat16*>(out),
+                                         static_cast<long>(ld_out), frames, heads, S);
+  else cudaLaunchKernelEx(&lc.cfg, pool_attn_kernel<__half>, reinterpret_cast<const __half*>(kv), static_cast<long>(ld_kv), q,
+                          reinterpret_cast<__half*>(out), static_cast<long>(ld_out), frames, heads, S);
   return check_launch("pool_attention");
 }
 

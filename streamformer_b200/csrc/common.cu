@@ -1,6 +1,7 @@
 // common.cu — error string, launch counter and small element-wise helpers shared by the library.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <vector>
@@ -56,6 +57,30 @@ int prof_collect(double* ms, double* flops, double* bytes, long long* launches, 
   return 0;
 }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }
+
+LaunchCfg::LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster) {
+  static const bool pdl = [] { const char* e = getenv("SF_PDL"); return !(e && e[0] == '0'); }();
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  int n = 0;
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = static_cast<unsigned>(n);
+}
 
 namespace {
 

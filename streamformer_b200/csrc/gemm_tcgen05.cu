@@ -7,9 +7,12 @@
 //   warp 0        TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
 //   warp 1        MMA issuer     (tcgen05.mma kind::f16, fp32 accumulators in TMEM; with CG=2 one
 //                                 256 x 256 x 16 instruction spans a CTA pair, cta_group::2)
-//   warps 2..     epilogue       (tcgen05.ld -> bias / GELU / pos+time embed / gated residual ->
-//                                 swizzled smem staging -> coalesced 16-byte global stores, optional
-//                                 (b,t,n)<->(b,n,t) row permutation)
+//   warp 2        aux            (one tile ahead: bias / LN column-sum slices and per-row LayerNorm
+//                                 statistics into shared memory, so the epilogue never waits on HBM)
+//   warps 4..     epilogue       (tcgen05.ld, thread == row -> folded LayerNorm / bias / GELU /
+//                                 pos+time embed / gated residual -> 256-bit global stores, one full
+//                                 sector per lane; optional (b,t,n)<->(b,n,t) row permutation; partial
+//                                 row statistics of the output for the next folded LayerNorm)
 //
 // TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
@@ -45,40 +48,45 @@ struct SmemLayout {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytesPerWarp = 2048 + 512;   // 32 rows x 64 B staging + bias slice (<=128 floats)
-  static constexpr int kEpiBytes = EW * kEpiBytesPerWarp;
-  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes;   // 227 KB minus slack, barriers, epilogue
+  // per accumulator stage, filled by the aux warp one tile ahead of the epilogue warps:
+  //   bias slice [BN] fp32 | LN column-sum slice [BN] fp32 | per-row (-mean, rstd) [128] float2
+  static constexpr int kAuxBias = 0;
+  static constexpr int kAuxColsum = BN * 4;
+  static constexpr int kAuxRows = 2 * BN * 4;
+  static constexpr int kAuxBytesPerStage = 2 * BN * 4 + kBM * 8;
+  static constexpr int kAuxBytes = 2 * kAuxBytesPerStage;
+  static constexpr int kBudget = 232448 - 1024 - 256 - kAuxBytes;   // 227 KB minus alignment slack, barriers, aux
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kEpiOffset = kBarOffset + 256;
-  static constexpr int kTotal = kEpiOffset + kEpiBytes + 1024;
+  static constexpr int kAuxOffset = kBarOffset + 256;
+  static constexpr int kTotal = kAuxOffset + kAuxBytes + 1024;
   static_assert(kStages >= 3, "not enough shared memory for a 3-stage pipeline");
-  static_assert(2 * kStages + 4 <= 32, "barrier area overflow");
+  static_assert(2 * kStages + 8 <= 31, "barrier area overflow");
 };
 
 template <typename T> struct UmmaFmt;
 template <> struct UmmaFmt<__half> { static constexpr int value = 0; };
 template <> struct UmmaFmt<__nv_bfloat16> { static constexpr int value = 1; };
 
-// Exact-erf GELU (hidden_act="gelu", reference ACT2FN["gelu"], …siglip.py:814-817) with erf from
-// Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16/fp16 output rounding):
-//   erf(z) = sign(z) * (1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2)),  t = 1/(1 + p|z|)
+// erf GELU (hidden_act="gelu", reference ACT2FN["gelu"], …siglip.py:814-817) as x * Phi(x) with
+// Phi(x) = 1 / (1 + 2^(x * P(x^2))), P the degree-5 minimax fit (in x^2) of -log2(e) * logit(Phi(x)) / x
+// on |x| <= 4.5 (gelu(-4.5) = -1.5e-5, Phi(4.5) = 1 - 3.4e-6).  Relative error of gelu <= 1.8e-4 on
+// the fitted range and absolute error <= 3.5e-5 everywhere, i.e. below the bf16 and fp16 output
+// rounding; 12 instructions with 2 MUFU (ex2, rcp) instead of the 19 of an Abramowitz-Stegun erf —
+// the fc1 epilogue is issue/MUFU-bound, not MMA-bound, otherwise.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float erf_z = copysignf(erf_abs, z);
-  const float h = 0.5f * x;
-  return fmaf(h, erf_z, h);
+  // only x^2 is clamped: beyond |x| = 4.5 the exponent keeps growing linearly in x with the slope
+  // reached at the boundary, so Phi still tends to 1 (x > 0) and to 0 faster than 1/|x| (x < 0)
+  const float t = fminf(x * x, 20.25f);
+  float p = fmaf(5.838623416e-08f, t, -3.653467351e-06f);
+  p = fmaf(p, t, 7.064459774e-05f);
+  p = fmaf(p, t, 5.841390203e-04f);
+  p = fmaf(p, t, -1.059873517e-01f);
+  p = fmaf(p, t, -2.301437105e+00f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * p));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return x * r;
 }
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
@@ -98,27 +106,68 @@ __device__ __forceinline__ int time_index(int t_abs, int time_len, int time_tota
   return s < time_len - 1 ? s : time_len - 1;
 }
 
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// output row of GEMM row m under the (b,t,n) <-> (b,n,t) permutations
+__device__ __forceinline__ long map_out_row(int m, int row_map, int Tn, int Sn) {
+  if (row_map == kRowBTNtoBNT) {
+    const int n = m % Sn, bt = m / Sn;
+    return (static_cast<long>(bt / Tn) * Sn + n) * Tn + bt % Tn;
+  }
+  if (row_map == kRowBNTtoBTN) {
+    const int t = m % Tn, bn = m / Tn;
+    return (static_cast<long>(bn / Sn) * Tn + t) * Sn + bn % Sn;
+  }
+  return m;
 }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 q;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
-  return q;
-}
+
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 q;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(addr));
   return q;
 }
+__device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// 16 consecutive 2-byte elements of one row <-> 8 registers.  `wide`: the row is 32-byte aligned, so
+// one 256-bit access (a full 32-byte sector per lane; sm_100 LDG/STG.256) moves them; otherwise two
+// 128-bit accesses.  ncols = valid columns at p (a multiple of 8; < 16 only on a ragged N edge).
+__device__ __forceinline__ void ldg_cols16(uint32_t (&v)[8], const void* p, int ncols, bool wide) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0u;
+  if (wide && ncols >= 16) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+  } else {
+    if (ncols >= 8) {
+      const uint4 q = *reinterpret_cast<const uint4*>(p);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+    if (ncols >= 16) {
+      const uint4 q = *(reinterpret_cast<const uint4*>(p) + 1);
+      v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+    }
+  }
+}
+__device__ __forceinline__ void stg_cols16(void* p, const uint32_t (&v)[8], int ncols, bool wide) {
+  if (wide && ncols >= 16) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+  } else {
+    if (ncols >= 8) *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+    if (ncols >= 16) *(reinterpret_cast<uint4*>(p) + 1) = make_uint4(v[4], v[5], v[6], v[7]);
+  }
+}
 
 template <typename T, int BN, int CG, int EPI, int EW>
-__global__ void __launch_bounds__(64 + EW * 32, 1)
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   using L = SmemLayout<BN, CG, EW>;
   constexpr int kStages = L::kStages;
   constexpr int kTileM = kBM * CG;
+  constexpr bool kLnCapable = (EPI == kEpiBias || EPI == kEpiAct);
+  constexpr bool kStatsCapable = (EPI == kEpiResidual || EPI == kEpiEmbed);
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -127,7 +176,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_full = tmem_empty + 2;
+  uint64_t* aux_empty = aux_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,6 +202,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], EW * CG);   // (leader's copy) epilogue warps of every CTA of the pair
+      mbar_init(&aux_full[a], 1);
+      mbar_init(&aux_empty[a], EW);
     }
     fence_barrier_init();
   }
@@ -167,6 +220,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the tail of the previous kernel; from here on we read its output
+  griddep_wait();
+  griddep_launch_dependents();
+
+  const GemmEpilogue& e = p.epi;
+  const bool ln = kLnCapable && e.ln_stats != nullptr;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (every CTA)
@@ -236,28 +295,103 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ aux warp
+    // Runs one tile ahead of the epilogue warps and stages everything their arithmetic needs that
+    // is not the accumulator, so no global-memory latency sits on the epilogue's critical path:
+    // the bias slice and the LN column-sum slice of the tile's BN columns, and for a folded
+    // LayerNorm (-mean, rstd) of the tile's 128 rows, reduced from the producer's partials.
+    const float inv_k = 1.0f / static_cast<float>(p.K);
+    int it = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * kTileM + static_cast<int>(cta_rank) * kBM;
+      const int n0 = (tile % n_tiles) * BN;
+      if constexpr (EPI == kEpiResidual) {
+        // pull the tile's residual rows into L2 a whole tile ahead of the epilogue's loads
+        const int left = p.N - n0;
+        const uint32_t bytes = static_cast<uint32_t>((left < BN ? left : BN) * 2) & ~15u;
+        const T* resb = reinterpret_cast<const T*>(e.residual);
+#pragma unroll
+        for (int rr = 0; rr < kBM / 32; ++rr) {
+          const int m = m0 + rr * 32 + lane;
+          if (m < p.M && bytes)
+            prefetch_l2_bulk(resb + map_out_row(m, e.row_map, e.T, e.S) * e.ldr + n0, bytes);
+        }
+      }
+      mbar_wait(&aux_empty[st], ph ^ 1);
+      const uint32_t aux_u = smem_u32(smem + L::kAuxOffset + st * L::kAuxBytesPerStage);
+#pragma unroll
+      for (int i = lane; i < BN / 4; i += 32) {
+        const int col = n0 + i * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = b4;
+        if (col < p.N) {
+          if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+          if (ln) c4 = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + col));
+        }
+        sts128f(aux_u + L::kAuxBias + i * 16, b4);
+        if constexpr (kLnCapable) sts128f(aux_u + L::kAuxColsum + i * 16, c4);
+      }
+      if constexpr (kLnCapable) {
+        if (ln) {
+          constexpr int kMaxParts = 12;
+#pragma unroll
+          for (int rr = 0; rr < kBM / 32; ++rr) {
+            const int row = rr * 32 + lane;
+            const int m = m0 + row;
+            float2 t[kMaxParts];
+#pragma unroll
+            for (int q = 0; q < kMaxParts; ++q) {
+              t[q] = make_float2(0.f, 0.f);
+              if (q < e.ln_parts && m < p.M) t[q] = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
+            }
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < kMaxParts; ++q) {
+              s1 += t[q].x;
+              s2 += t[q].y;
+            }
+            for (int q = kMaxParts; q < e.ln_parts; ++q) {   // (never with the shipped tile shapes)
+              if (m < p.M) {
+                const float2 u = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
+                s1 += u.x;
+                s2 += u.y;
+              }
+            }
+            const float mean = s1 * inv_k;
+            const float var = fmaxf(fmaf(s2, inv_k, -mean * mean), 0.f);
+            const float rstd = rsqrtf(var + e.ln_eps);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(aux_u + L::kAuxRows + row * 8), "f"(-mean), "f"(rstd)
+                         : "memory");
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aux_full[st]);
+    }
+  } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue warps
-    // Each warp owns 32 accumulator rows (its TMEM lane quarter) x kColsPerWarp columns and walks
-    // them in 32-column chunks, software-pipelined (the tcgen05.ld of chunk c+1 is in flight while
-    // chunk c is processed):  TMEM -> bias/act/embed/residual in the thread==row layout -> 2 KB
-    // swizzled smem staging -> 16-byte global stores in an (8 rows x 64 B) coalesced layout.
-    // Residual rows travel the same staging buffer in the opposite direction first.
-    const int ew = warp - 2;
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter, thread == row) x kColsPerWarp
+    // columns and walks them in 32-column chunks, software-pipelined: the tcgen05.ld of chunk c+1
+    // and the residual loads of chunk c+1 are in flight while chunk c is processed.  A thread's 32
+    // outputs of a chunk are 64 contiguous bytes of its row: they leave as two 256-bit stores (one
+    // full 32-byte sector each), so no shared-memory transpose is needed; the residual arrives the
+    // same way.
+    const int ew = warp - 4;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int colgrp = ew >> 2;            // which slice of the BN columns
     constexpr int kColsPerWarp = BN / (EW / 4);
-    constexpr int kChunks = kColsPerWarp / 32;
-    const uint32_t stage_u = smem_u32(smem + L::kEpiOffset + ew * L::kEpiBytesPerWarp);
-    const uint32_t bias_u = stage_u + 2048;
-    const GemmEpilogue& e = p.epi;
+    constexpr int kCW = (EW == 16) ? 16 : 32;       // chunk width: 16 warps have half the registers each
+    constexpr int kChunks = kColsPerWarp / kCW;
+    constexpr int kPieces = kCW / 16;               // 16-column (32-byte) pieces per chunk
+    static_assert(kChunks % 2 == 0, "chunks are processed in double-buffered pairs");
+    const bool want_stats = kStatsCapable && e.stats_out != nullptr;
     const float gscale = e.gate ? tanhf(__ldg(e.gate)) : 1.0f;
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(e.residual);
-    const int crow0 = lane >> 2, cchunk = lane & 3;   // coalesced layout: rows crow0 + 8*i, 16-byte chunk cchunk
-    auto stage_addr = [&](int row, int ch) -> uint32_t {
-      return stage_u + static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
-    };
+    const bool wide_out = ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) && (p.ldo % 16 == 0);
+    const bool wide_res = ((reinterpret_cast<uintptr_t>(e.residual) & 31) == 0) && (e.ldr % 16 == 0);
     int it = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int acc = it & 1;
@@ -291,114 +425,149 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (e.time_emb)
           time_row = e.time_emb + static_cast<long>(time_index(e.time_off + frame, e.time_len, e.time_total)) * p.N;
       }
-      // output rows handled by this lane in the coalesced layout (-1 = out of range)
-      const int r_own = row_ok ? static_cast<int>(r) : -1;
-      int r_c[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) r_c[i] = __shfl_sync(0xffffffffu, r_own, crow0 + 8 * i);
       const int wcol0 = n0 + colgrp * kColsPerWarp;
-      // this warp's bias slice -> smem (overlaps the MMAs of this tile)
-      if (lane * 4 < kColsPerWarp) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int bc = wcol0 + lane * 4;
-        if (e.bias && bc < p.N) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + bc));
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias_u + lane * 16), "f"(b4.x), "f"(b4.y),
-                     "f"(b4.z), "f"(b4.w) : "memory");
+      T* orow = out + r * p.ldo;
+      const T* rrow = res + r * e.ldr;
+      // valid columns (multiple of 8) of the 16-column piece starting at `col`
+      auto ncols_at = [&](int col) -> int {
+        if (!row_ok) return 0;
+        const int left = p.N - col;
+        return left >= 16 ? 16 : (left > 0 ? left : 0);
+      };
+      uint32_t rbuf[2][kPieces][8];
+      if constexpr (EPI == kEpiResidual) {
+#pragma unroll
+        for (int q = 0; q < kPieces; ++q) ldg_cols16(rbuf[0][q], rrow + wcol0 + q * 16, ncols_at(wcol0 + q * 16), wide_res);
       }
-      __syncwarp();
+      const uint32_t aux_u = smem_u32(smem + L::kAuxOffset + acc * L::kAuxBytesPerStage);
+      const uint32_t bias_u = aux_u + L::kAuxBias + colgrp * kColsPerWarp * 4;
+      const uint32_t csum_u = aux_u + L::kAuxColsum + colgrp * kColsPerWarp * 4;
+      mbar_wait(&aux_full[acc], acc_phase);
+      float nmean = 0.f, rstd = 1.f;
+      if constexpr (kLnCapable) {
+        if (ln) {
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(nmean), "=f"(rstd)
+                       : "r"(aux_u + L::kAuxRows + (quarter * 32 + lane) * 8));
+        }
+      }
+      float st1 = 0.f, st2 = 0.f;   // partial (sum, sumsq) of this row's output columns
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
                               colgrp * kColsPerWarp;
-      uint32_t raw[2][32];
-      tmem_ld_32x32b_x32(t_base, raw[0]);
+      uint32_t raw[2][kCW];
+      auto tmem_fetch = [&](int c, uint32_t (&dst)[kCW]) {
+        if constexpr (kCW == 32) tmem_ld_32x32b_x32(t_base + c * kCW, dst);
+        else tmem_ld_32x32b_x16(t_base + c * kCW, dst);
+      };
+      tmem_fetch(0, raw[0]);
+      // pairs of chunks (the two register buffers); the pair loop itself is not unrolled to keep the
+      // epilogue's code inside the instruction cache
+#pragma unroll 1
+      for (int cp = 0; cp < kChunks / 2; ++cp) {
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int col0 = wcol0 + c * 32;
-        const int ccol = col0 + cchunk * 8;
-        const bool ccol_ok = ccol < p.N;
-        uint4 rr[4];
-        if constexpr (EPI == kEpiResidual) {
+        for (int h = 0; h < 2; ++h) {
+          const int c = cp * 2 + h;
+          const int col0 = wcol0 + c * kCW;
+          tmem_ld_wait();                                     // chunk c is in registers
+          if (c + 1 < kChunks) {
+            tmem_fetch(c + 1, raw[h ^ 1]);
+            if constexpr (EPI == kEpiResidual) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            rr[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (r_c[i] >= 0 && ccol_ok)
-              rr[i] = *reinterpret_cast<const uint4*>(res + static_cast<long>(r_c[i]) * e.ldr + ccol);
-          }
-        }
-        float4 bb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bb[j] = lds128f(bias_u + (c * 32 + j * 4) * 4);
-        tmem_ld_wait();                                     // chunk c is in registers
-        if (c + 1 < kChunks) tmem_ld_32x32b_x32(t_base + (c + 1) * 32, raw[(c + 1) & 1]);
-        if constexpr (EPI == kEpiResidual) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sts128(stage_addr(crow0 + 8 * i, cchunk), rr[i].x, rr[i].y, rr[i].z, rr[i].w);
-          __syncwarp();
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns
-          float vv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = __uint_as_float(raw[c & 1][g * 8 + j]);
-          vv[0] += bb[2 * g].x; vv[1] += bb[2 * g].y; vv[2] += bb[2 * g].z; vv[3] += bb[2 * g].w;
-          vv[4] += bb[2 * g + 1].x; vv[5] += bb[2 * g + 1].y; vv[6] += bb[2 * g + 1].z; vv[7] += bb[2 * g + 1].w;
-          if constexpr (EPI == kEpiAct) {
-            if (e.act == kActGeluErf) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
+              for (int q = 0; q < kPieces; ++q)
+                ldg_cols16(rbuf[h ^ 1][q], rrow + col0 + kCW + q * 16, ncols_at(col0 + kCW + q * 16), wide_res);
             }
           }
-          if constexpr (EPI == kEpiEmbed) {
-            const int col = col0 + g * 8;
-            if (pos_row && row_ok && col < p.N) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + col + 4));
+          uint32_t ob[kPieces][8];
+#pragma unroll
+          for (int g = 0; g < kCW / 8; ++g) {  // groups of 8 columns
+            float vv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = __uint_as_float(raw[h][g * 8 + j]);
+            const float4 b0 = lds128f(bias_u + (c * kCW + g * 8) * 4);
+            const float4 b1 = lds128f(bias_u + (c * kCW + g * 8 + 4) * 4);
+            bool did_ln = false;
+            if constexpr (kLnCapable) {
+              if (ln) {
+                const float4 c0 = lds128f(csum_u + (c * kCW + g * 8) * 4);
+                const float4 c1 = lds128f(csum_u + (c * kCW + g * 8 + 4) * 4);
+                vv[0] = fmaf(rstd, fmaf(nmean, c0.x, vv[0]), b0.x); vv[1] = fmaf(rstd, fmaf(nmean, c0.y, vv[1]), b0.y);
+                vv[2] = fmaf(rstd, fmaf(nmean, c0.z, vv[2]), b0.z); vv[3] = fmaf(rstd, fmaf(nmean, c0.w, vv[3]), b0.w);
+                vv[4] = fmaf(rstd, fmaf(nmean, c1.x, vv[4]), b1.x); vv[5] = fmaf(rstd, fmaf(nmean, c1.y, vv[5]), b1.y);
+                vv[6] = fmaf(rstd, fmaf(nmean, c1.z, vv[6]), b1.z); vv[7] = fmaf(rstd, fmaf(nmean, c1.w, vv[7]), b1.w);
+                did_ln = true;
+              }
+            }
+            if (!did_ln) {
               vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
               vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
             }
-            if (time_row && row_ok && col < p.N) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(time_row + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(time_row + col + 4));
-              vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-              vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+            if constexpr (EPI == kEpiAct) {
+              if (e.act == kActGeluErf) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
+              }
+            }
+            if constexpr (EPI == kEpiEmbed) {
+              const int col = col0 + g * 8;
+              if (pos_row && row_ok && col < p.N) {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(pos_row + col));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(pos_row + col + 4));
+                vv[0] += q0.x; vv[1] += q0.y; vv[2] += q0.z; vv[3] += q0.w;
+                vv[4] += q1.x; vv[5] += q1.y; vv[6] += q1.z; vv[7] += q1.w;
+              }
+              if (time_row && row_ok && col < p.N) {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(time_row + col));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(time_row + col + 4));
+                vv[0] += q0.x; vv[1] += q0.y; vv[2] += q0.z; vv[3] += q0.w;
+                vv[4] += q1.x; vv[5] += q1.y; vv[6] += q1.z; vv[7] += q1.w;
+              }
+            }
+            if constexpr (EPI == kEpiResidual) {
+              const uint32_t* rq = &rbuf[h][g >> 1][(g & 1) * 4];
+              const float2 r0 = Pack2<T>::unpack(rq[0]), r1 = Pack2<T>::unpack(rq[1]);
+              const float2 r2 = Pack2<T>::unpack(rq[2]), r3 = Pack2<T>::unpack(rq[3]);
+              vv[0] = fmaf(gscale, vv[0], r0.x); vv[1] = fmaf(gscale, vv[1], r0.y);
+              vv[2] = fmaf(gscale, vv[2], r1.x); vv[3] = fmaf(gscale, vv[3], r1.y);
+              vv[4] = fmaf(gscale, vv[4], r2.x); vv[5] = fmaf(gscale, vv[5], r2.y);
+              vv[6] = fmaf(gscale, vv[6], r3.x); vv[7] = fmaf(gscale, vv[7], r3.y);
+            } else if constexpr (EPI == kEpiBias) {
+              if (e.gate) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] *= gscale;
+              }
+            }
+            uint32_t* oq = &ob[g >> 1][(g & 1) * 4];
+            oq[0] = Pack2<T>::pack(vv[0], vv[1]); oq[1] = Pack2<T>::pack(vv[2], vv[3]);
+            oq[2] = Pack2<T>::pack(vv[4], vv[5]); oq[3] = Pack2<T>::pack(vv[6], vv[7]);
+            if constexpr (kStatsCapable) {
+              if (want_stats) {   // statistics of the values as stored (rounded), what the next GEMM multiplies
+                const float2 q0 = Pack2<T>::unpack(oq[0]), q1 = Pack2<T>::unpack(oq[1]);
+                const float2 q2 = Pack2<T>::unpack(oq[2]), q3 = Pack2<T>::unpack(oq[3]);
+                st1 += ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+                st2 = fmaf(q0.x, q0.x, fmaf(q0.y, q0.y, fmaf(q1.x, q1.x, fmaf(q1.y, q1.y, st2))));
+                st2 = fmaf(q2.x, q2.x, fmaf(q2.y, q2.y, fmaf(q3.x, q3.x, fmaf(q3.y, q3.y, st2))));
+              }
             }
           }
-          const uint32_t my = stage_addr(lane, g);
-          if constexpr (EPI == kEpiResidual) {
-            const uint4 q = lds128(my);
-            const float2 r0 = Pack2<T>::unpack(q.x), r1 = Pack2<T>::unpack(q.y);
-            const float2 r2 = Pack2<T>::unpack(q.z), r3 = Pack2<T>::unpack(q.w);
-            vv[0] = fmaf(gscale, vv[0], r0.x); vv[1] = fmaf(gscale, vv[1], r0.y);
-            vv[2] = fmaf(gscale, vv[2], r1.x); vv[3] = fmaf(gscale, vv[3], r1.y);
-            vv[4] = fmaf(gscale, vv[4], r2.x); vv[5] = fmaf(gscale, vv[5], r2.y);
-            vv[6] = fmaf(gscale, vv[6], r3.x); vv[7] = fmaf(gscale, vv[7], r3.y);
-          } else if constexpr (EPI == kEpiBias) {
-            if (e.gate) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) vv[j] *= gscale;
-            }
-          }
-          sts128(my, Pack2<T>::pack(vv[0], vv[1]), Pack2<T>::pack(vv[2], vv[3]), Pack2<T>::pack(vv[4], vv[5]),
-                 Pack2<T>::pack(vv[6], vv[7]));
+          for (int q = 0; q < kPieces; ++q) stg_cols16(orow + col0 + q * 16, ob[q], ncols_at(col0 + q * 16), wide_out);
         }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 q = lds128(stage_addr(crow0 + 8 * i, cchunk));
-          if (r_c[i] >= 0 && ccol_ok) *reinterpret_cast<uint4*>(out + static_cast<long>(r_c[i]) * p.ldo + ccol) = q;
-        }
-        __syncwarp();  // staging buffer is reused by the next chunk
       }
-      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+      if constexpr (kStatsCapable) {
+        if (want_stats && row_ok)
+          e.stats_out[static_cast<long>(wcol0 / kColsPerWarp) * p.M + r] = make_float2(st1, st2);
+      }
+      // all TMEM reads of this accumulator and all reads of the aux stage are complete -> hand both back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive(&aux_empty[acc]);
       }
     }
   }
@@ -488,24 +657,13 @@ int launch_gemm(cudaStream_t stream, int dtype, const void* A, int lda, const vo
   const int tiles = m_tiles * n_tiles;
   const int max_workers = num_sms() / CG;
   const int workers = tiles < max_workers ? tiles : max_workers;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(workers * CG));
-  cfg.blockDim = dim3(64 + EW * 32);
-  cfg.dynamicSmemBytes = L::kTotal;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  LaunchCfg lc(dim3(static_cast<unsigned>(workers * CG)), dim3(128 + EW * 32), L::kTotal, stream, CG);
   cudaError_t e;
   {
     ProfScope ps(stream, kProfGemm, 2.0 * p.M * p.N * p.K,
                  2.0 * (static_cast<double>(p.M) * p.K + static_cast<double>(p.N) * p.K +
                         static_cast<double>(p.M) * p.N * (p.epi.residual ? 2 : 1)));
-    e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p);
+    e = cudaLaunchKernelEx(&lc.cfg, kernel, tmA, tmB, p);
   }
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
@@ -521,22 +679,44 @@ int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// Tile shape for an M x N output: 0 -> 256 x 256 on CTA pairs (cta_group::2: half the B traffic per
+// CTA) when that fills the machine, 1 -> 128 x 256 single-CTA tiles, 2 -> 128 x 128 for small
+// problems (more CTAs in flight).  SF_GEMM_MODE=1 forces single-CTA tiles (debug / A-B comparison).
+int pick_shape(int M, int N) {
+  static const int mode = env_int("SF_GEMM_MODE", 0);
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const int m_tiles2 = (M + 2 * kBM - 1) / (2 * kBM);
+  const int n_tiles = (N + 255) / 256;
+  if (mode != 1 && N >= 256 && m_tiles2 * n_tiles >= num_sms() / 2) return 0;
+  if (N >= 256 && m_tiles * n_tiles >= num_sms()) return 1;
+  return 2;
+}
+// Epilogue warps: 16 (four per scheduler, 16-column chunks) for the GELU epilogue, whose MUFU/FMA
+// latency two warps per scheduler cannot hide (fc1: 114 -> 102 us); 8 otherwise (measured equal or better).
+// SF_GEMM_EW=8|16 forces one choice (A-B comparison).
+int pick_epi_warps(int epi_mode, const GemmEpilogue& e) {
+  static const int forced = env_int("SF_GEMM_EW", 0);
+  if (forced == 8 || forced == 16) return forced;
+  (void)e;
+  return epi_mode == kEpiAct ? 16 : 8;
+}
+
 template <typename T, int EPI>
 int dispatch_shape(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw,
                    const GemmParams& p) {
-  // 256x256 tiles on CTA pairs (cta_group::2: half the B traffic per CTA) when they fill the machine,
-  // 128x256 single-CTA tiles next, 128x128 for small problems (more CTAs in flight).
-  // SF_GEMM_MODE=1 forces single-CTA tiles (debug / A-B comparison).
-  static const int mode = env_int("SF_GEMM_MODE", 0);
-  constexpr int EW = 8;
-  const int m_tiles = (p.M + kBM - 1) / kBM;
-  const int m_tiles2 = (p.M + 2 * kBM - 1) / (2 * kBM);
-  const int n_tiles = (p.N + 255) / 256;
-  const bool pair = mode != 1 && (p.N >= 256) && (m_tiles2 * n_tiles >= num_sms() / 2);
-  const bool wide = (p.N >= 256) && (m_tiles * n_tiles >= num_sms());
-  if (pair) return launch_gemm<T, 256, 2, EPI, EW>(stream, dtype, A, lda, W, ldw, p);
-  if (wide) return launch_gemm<T, 256, 1, EPI, EW>(stream, dtype, A, lda, W, ldw, p);
-  return launch_gemm<T, 128, 1, EPI, EW>(stream, dtype, A, lda, W, ldw, p);
+  const int shape = pick_shape(p.M, p.N);
+  if (pick_epi_warps(EPI, p.epi) == 16) {
+    switch (shape) {
+      case 0: return launch_gemm<T, 256, 2, EPI, 16>(stream, dtype, A, lda, W, ldw, p);
+      case 1: return launch_gemm<T, 256, 1, EPI, 16>(stream, dtype, A, lda, W, ldw, p);
+      default: return launch_gemm<T, 128, 1, EPI, 16>(stream, dtype, A, lda, W, ldw, p);
+    }
+  }
+  switch (shape) {
+    case 0: return launch_gemm<T, 256, 2, EPI, 8>(stream, dtype, A, lda, W, ldw, p);
+    case 1: return launch_gemm<T, 256, 1, EPI, 8>(stream, dtype, A, lda, W, ldw, p);
+    default: return launch_gemm<T, 128, 1, EPI, 8>(stream, dtype, A, lda, W, ldw, p);
+  }
 }
 
 template <typename T>
@@ -560,6 +740,15 @@ int dispatch_epilogue(cudaStream_t stream, int dtype, const void* A, int lda, co
 
 }  // namespace
 
+int gemm_stats_parts(int M, int N) {
+  // stats_out comes from the residual / embed epilogues, which run with 8 epilogue warps unless forced
+  static const int forced = env_int("SF_GEMM_EW", 0);
+  const int ew = forced == 16 ? 16 : 8;
+  const int bn = pick_shape(M, N) == 2 ? 128 : 256;
+  const int cols_per_part = bn / (ew / 4);
+  return (N + cols_per_part - 1) / cols_per_part;
+}
+
 int gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out,
          int ldo, int M, int N, int K, const GemmEpilogue& epi) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -570,6 +759,14 @@ int gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, 
   }
   if (dtype != kBF16 && dtype != kF16) {
     set_error("gemm: dtype must be bf16 or f16");
+    return -1;
+  }
+  if (epi.ln_stats && (epi.residual || epi.pos || epi.time_emb || !epi.ln_colsum || epi.ln_parts <= 0)) {
+    set_error("gemm: a folded LayerNorm needs ln_colsum/ln_parts and cannot be combined with residual/embed epilogues");
+    return -1;
+  }
+  if (epi.stats_out && !(epi.residual || epi.pos || epi.time_emb)) {
+    set_error("gemm: stats_out is produced by the residual / embed epilogues only");
     return -1;
   }
   GemmParams p;

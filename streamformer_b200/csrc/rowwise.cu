@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(256, 5)
 layernorm_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, T* __restrict__ y, int ldy, int M, int D,
                  int row_map, int Tn, int Sn) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int nchunks = D >> 3;
   const long m = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(256)
 layernorm_wide_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, T* __restrict__ y, int ldy, int M, int D,
                       int row_map, int Tn, int Sn) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int nchunks = D >> 3;
   const long m = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -131,11 +135,39 @@ void launch_layernorm(cudaStream_t stream, const void* x, int ldx, const float* 
   const unsigned blocks = static_cast<unsigned>((static_cast<long>(M) + wpb - 1) / wpb);
   const T* xi = reinterpret_cast<const T*>(x);
   T* yo = reinterpret_cast<T*>(y);
-  if (D <= 256) layernorm_kernel<T, 1><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
-  else if (D <= 512) layernorm_kernel<T, 2><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
-  else if (D <= 768) layernorm_kernel<T, 3><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
-  else if (D <= 1024) layernorm_kernel<T, 4><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
-  else layernorm_wide_kernel<T><<<blocks, threads, 0, stream>>>(xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn);
+  LaunchCfg lc(dim3(blocks), dim3(threads), 0, stream);
+#define SF_LN_ARGS xi, ldx, gamma, beta, eps, yo, ldy, M, D, row_map, Tn, Sn
+  if (D <= 256) cudaLaunchKernelEx(&lc.cfg, layernorm_kernel<T, 1>, SF_LN_ARGS);
+  else if (D <= 512) cudaLaunchKernelEx(&lc.cfg, layernorm_kernel<T, 2>, SF_LN_ARGS);
+  else if (D <= 768) cudaLaunchKernelEx(&lc.cfg, layernorm_kernel<T, 3>, SF_LN_ARGS);
+  else if (D <= 1024) cudaLaunchKernelEx(&lc.cfg, layernorm_kernel<T, 4>, SF_LN_ARGS);
+  else cudaLaunchKernelEx(&lc.cfg, layernorm_wide_kernel<T>, SF_LN_ARGS);
+#undef SF_LN_ARGS
+}
+
+// (sum, sum of squares) of every row, one warp per row: the one-partial statistics table a folded
+// LayerNorm consumes when its input was not produced by gemm() (GemmEpilogue::ln_stats).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const T* __restrict__ x, int ldx, int M, int D, float2* __restrict__ stats) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const long m = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const T* xr = x + m * ldx;
+  float s1 = 0.f, s2 = 0.f, f[8];
+  for (int c = lane; c < (D >> 3); c += 32) {
+    unpack8<T>(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1 += f[j];
+      s2 = fmaf(f[j], f[j], s2);
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) stats[m] = make_float2(s1, s2);
 }
 
 template <typename PixT>
@@ -171,6 +203,8 @@ __device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
 template <typename PixT, typename T>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int BT, int C, int H, int W, int P) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int gw = W / P, gh = H / P;
   const int S = gw * gh;
   const int K = C * P * P;
@@ -207,8 +241,9 @@ int launch_im2col(cudaStream_t st, const void* pix, void* out, int BT, int C, in
   if (blocks < 1) blocks = 1;
   {
     ProfScope ps(st, kProfIm2col, 0.0, static_cast<double>(total) * 8 * (sizeof(PixT) + sizeof(T)));
-    im2col_kernel<PixT, T><<<static_cast<int>(blocks), 256, 0, st>>>(
-        reinterpret_cast<const PixT*>(pix), reinterpret_cast<T*>(out), BT, C, H, W, P);
+    LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st);
+    cudaLaunchKernelEx(&lc.cfg, im2col_kernel<PixT, T>, reinterpret_cast<const PixT*>(pix), reinterpret_cast<T*>(out),
+                       BT, C, H, W, P);
   }
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -237,6 +272,23 @@ int layernorm(cudaStream_t stream, int dtype, const void* x, int ldx, const floa
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("layernorm launch: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+int rowstats(cudaStream_t stream, int dtype, const void* x, int ldx, int M, int D, float2* stats) {
+  if (M <= 0) return 0;
+  if ((D % 8) || (ldx % 8)) { set_error("rowstats: D and ldx must be multiples of 8"); return -1; }
+  if (dtype != kBF16 && dtype != kF16) { set_error("rowstats: dtype must be bf16 or f16"); return -1; }
+  const unsigned blocks = static_cast<unsigned>((static_cast<long>(M) + 7) / 8);
+  {
+    ProfScope ps(stream, kProfLayerNorm, 0.0, 2.0 * static_cast<double>(M) * D);
+    LaunchCfg lc(dim3(blocks), dim3(256), 0, stream);
+    if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, rowstats_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, D, stats);
+    else cudaLaunchKernelEx(&lc.cfg, rowstats_kernel<__half>, reinterpret_cast<const __half*>(x), ldx, M, D, stats);
+  }
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("rowstats launch: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 

@@ -75,6 +75,35 @@ __global__ void matvec_kernel(float* __restrict__ y, const float* __restrict__ W
   if (lane == 0) y[o] = scale * (acc + (b ? b[o] : 0.f));
 }
 
+// LayerNorm folded into the next projection (bind time):  LN(x) . W^T + b  ==
+//   rstd * (x . W'^T - mean * colsum) + b'   with W'[n,k] = W[n,k] * gamma[k] (rounded to the
+//   activation dtype), colsum[n] = sum_k W'[n,k] (of the ROUNDED values, so the mean term cancels
+//   exactly against what the tensor cores accumulate) and b'[n] = b[n] + sum_k W[n,k] * beta[k].
+// One warp per output row n.
+template <typename T>
+__global__ void ln_fold_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ bias,
+                               T* __restrict__ Wp, float* __restrict__ colsum, float* __restrict__ biasp,
+                               int O, int I) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= O) return;
+  float cs = 0.f, bs = 0.f;
+  for (int i = lane; i < I; i += 32) {
+    const float w = W[static_cast<long>(o) * I + i];
+    const T wr = static_cast<T>(w * gamma[i]);
+    Wp[static_cast<long>(o) * I + i] = wr;
+    cs += static_cast<float>(wr);
+    bs += w * beta[i];
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[o] = cs;
+    biasp[o] = (bias ? bias[o] : 0.f) + bs;
+  }
+}
+
 struct Bump {
   uint8_t* base = nullptr;
   size_t size = 0, off = 0;
@@ -98,6 +127,8 @@ struct LayerW {
   float *s_qkv_b = nullptr, *s_out_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
   float *ln_t_g = nullptr, *ln_t_b = nullptr, *ln_s_g = nullptr, *ln_s_b = nullptr;
   float *ln_a_g = nullptr, *ln_a_b = nullptr;
+  // column sums of the gamma-scaled matrices (folded LayerNorms); t_qkv_b / s_qkv_b / fc1_b hold b + W.beta
+  float *t_qkv_cs = nullptr, *s_qkv_cs = nullptr, *fc1_cs = nullptr;
   float* gate = nullptr;
 };
 
@@ -135,23 +166,30 @@ struct sf_kv {
 namespace {
 
 struct WsPlan {
-  void *ln, *qkv, *ctx, *tmp, *mlp;
+  void *qkv, *ctx, *tmp, *mlp;
+  // partial row statistics (sum, sumsq) feeding the folded LayerNorms: [0] after the temporal
+  // branch, [1] after the spatial branch, [2] at the layer boundary (after the MLP / the embedding)
+  float2* stats[3];
 };
+
+size_t stats_bytes(const sf_ctx* c, long M) {
+  return static_cast<size_t>(gemm_stats_parts_max(c->D)) * static_cast<size_t>(M) * sizeof(float2);
+}
 
 size_t layer_ws_bytes(const sf_ctx* c, long M) {
   const size_t es = 2;
   const size_t D = c->D, I = c->I;
-  // ln[M,D] qkv[M,3D] ctx[M,D] tmp[M,D] mlp[M,I]  (+256 B alignment each)
-  return static_cast<size_t>(M) * (D + 3 * D + D + D + I) * es + 5 * 256;
+  // qkv[M,3D] ctx[M,D] tmp[M,D] mlp[M,I] stats[3]  (+256 B alignment each)
+  return static_cast<size_t>(M) * (3 * D + D + D + I) * es + 3 * stats_bytes(c, M) + 7 * 256;
 }
 
 int carve_layer_ws(const sf_ctx* c, long M, Bump& b, WsPlan& p) {
   const size_t es = 2, D = c->D, I = c->I;
-  p.ln = b.take(M * D * es);
   p.qkv = b.take(M * 3 * D * es);
   p.ctx = b.take(M * D * es);
   p.tmp = b.take(M * D * es);
   p.mlp = b.take(M * I * es);
+  for (int i = 0; i < 3; ++i) p.stats[i] = static_cast<float2*>(b.take(stats_bytes(c, M)));
   if (b.overflow) {
     set_error("workspace too small: need at least %zu bytes, have %zu", b.off, b.size);
     return SF_ERR_WORKSPACE;
@@ -165,18 +203,32 @@ GemmEpilogue epi_bias(const float* bias) {
   return e;
 }
 
+GemmEpilogue epi_ln(const float* bias, const float* colsum, const float2* stats, int parts, float eps) {
+  GemmEpilogue e;
+  e.bias = bias;
+  e.ln_colsum = colsum; e.ln_stats = stats; e.ln_parts = parts; e.ln_eps = eps;
+  return e;
+}
+
+// One divided space-time block.  Rows stay in the residual stream's (b,n,t) order throughout: the
+// temporal branch sees its T frames of a site as consecutive rows, the spatial attention reads the
+// S tokens of a frame in place with a row stride of T (no permute copies, reference :962-991).
+// The three LayerNorms are folded into the QKV / fc1 GEMMs (GemmEpilogue::ln_stats); the row
+// statistics they need are by-products of the epilogues that wrote the rows:
+//   st_in (x_in) -> temporal QKV ; w.stats[0] (after temporal) -> spatial QKV ;
+//   w.stats[1] (after spatial) -> fc1 ; st_out (after the MLP) -> the next layer.
 int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, int B, int T, int S,
-              sf_kv* kv, float* probs, const WsPlan& w) {
+              sf_kv* kv, float* probs, const WsPlan& w, const float2* st_in, int parts_in, float2* st_out) {
   const LayerW& lw = c->layers[l];
   const int D = c->D, I = c->I, H = c->H, dt = c->cfg.dtype;
   const long M = static_cast<long>(B) * S * T;
   const float eps = c->cfg.layer_norm_eps;
   const float scale = 0.125f;  // head_dim**-0.5, head_dim == 64 (…siglip.py:512, 628)
-  const bool permute = T > 1;
+  const int parts_d = gemm_stats_parts(static_cast<int>(M), D);
 
   // ---- temporal branch (…siglip.py:937-958): rows (b,n,t), T innermost => sites are contiguous
-  SF_CHECK(layernorm(st, dt, x_in, D, lw.ln_t_g, lw.ln_t_b, eps, w.ln, D, M, D, kRowIdentity, T, S));
-  SF_CHECK(gemm(st, dt, w.ln, D, lw.t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D, epi_bias(lw.t_qkv_b)));
+  SF_CHECK(gemm(st, dt, x_in, D, lw.t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
+                epi_ln(lw.t_qkv_b, lw.t_qkv_cs, st_in, parts_in, eps)));
   if (kv) {
     SF_CHECK(kv_append(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, B * S, H, T, kv->seen));
     SF_CHECK(temporal_attention(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, w.ctx, D, B * S, H, T,
@@ -188,6 +240,7 @@ int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, 
   {
     GemmEpilogue e;
     e.residual = x_in; e.ldr = D; e.gate = lw.gate;
+    e.stats_out = w.stats[0];
     if (c->cfg.fold_temporal_proj) {
       e.bias = lw.t_fold_b;
       SF_CHECK(gemm(st, dt, w.ctx, D, lw.t_fold_w, D, x_out, D, M, D, D, e));
@@ -197,38 +250,33 @@ int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, 
       SF_CHECK(gemm(st, dt, w.tmp, D, lw.t_dense_w, D, x_out, D, M, D, D, e));
     }
   }
-  // ---- spatial branch (…siglip.py:960-996): QKV GEMM writes rows in (b,t,n) order, the out-proj
-  // epilogue maps them back onto the (b,n,t) residual — no permute copies.
-  SF_CHECK(layernorm(st, dt, x_out, D, lw.ln_s_g, lw.ln_s_b, eps, w.ln, D, M, D, kRowIdentity, T, S));
-  {
-    GemmEpilogue e = epi_bias(lw.s_qkv_b);
-    if (permute) { e.row_map = kRowBNTtoBTN; e.T = T; e.S = S; }
-    SF_CHECK(gemm(st, dt, w.ln, D, lw.s_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D, e));
-  }
-  SF_CHECK(spatial_attention(st, dt, w.qkv, 3 * D, w.ctx, D, B * T, H, S, scale, probs));
+  // ---- spatial branch (…siglip.py:960-996)
+  SF_CHECK(gemm(st, dt, x_out, D, lw.s_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
+                epi_ln(lw.s_qkv_b, lw.s_qkv_cs, w.stats[0], parts_d, eps)));
+  SF_CHECK(spatial_attention(st, dt, w.qkv, 3 * D, w.ctx, D, B * T, H, S, T, scale, probs));
   {
     GemmEpilogue e = epi_bias(lw.s_out_b);
     e.residual = x_out; e.ldr = D;
-    if (permute) { e.row_map = kRowBTNtoBNT; e.T = T; e.S = S; }
+    e.stats_out = w.stats[1];
     SF_CHECK(gemm(st, dt, w.ctx, D, lw.s_out_w, D, x_out, D, M, D, D, e));
   }
   // ---- MLP (…siglip.py:997-1000)
-  SF_CHECK(layernorm(st, dt, x_out, D, lw.ln_a_g, lw.ln_a_b, eps, w.ln, D, M, D, kRowIdentity, T, S));
   {
-    GemmEpilogue e = epi_bias(lw.fc1_b);
+    GemmEpilogue e = epi_ln(lw.fc1_b, lw.fc1_cs, w.stats[1], parts_d, eps);
     e.act = c->cfg.hidden_act;
-    SF_CHECK(gemm(st, dt, w.ln, D, lw.fc1_w, D, w.mlp, I, M, I, D, e));
+    SF_CHECK(gemm(st, dt, x_out, D, lw.fc1_w, D, w.mlp, I, M, I, D, e));
   }
   {
     GemmEpilogue e = epi_bias(lw.fc2_b);
     e.residual = x_out; e.ldr = D;
+    e.stats_out = st_out;
     SF_CHECK(gemm(st, dt, w.mlp, I, lw.fc2_w, I, x_out, D, M, D, I, e));
   }
   return 0;
 }
 
 int run_embed(sf_ctx* c, cudaStream_t st, const void* pixels, int pix_dtype, int B, int T, int Hh, int Ww,
-              int time_off, int time_total, void* x_out, void* patches) {
+              int time_off, int time_total, void* x_out, void* patches, float2* stats_out) {
   const int P = c->cfg.patch_size, C = c->cfg.num_channels, D = c->D, dt = c->cfg.dtype;
   const int S = (Hh / P) * (Ww / P);
   const float* pos = nullptr;
@@ -245,6 +293,7 @@ int run_embed(sf_ctx* c, cudaStream_t st, const void* pixels, int pix_dtype, int
   e.row_map = kRowBTNtoBNT; e.T = T; e.S = S;
   e.pos = pos;
   e.time_emb = c->time_emb; e.time_len = c->cfg.num_frames; e.time_total = time_total; e.time_off = time_off;
+  e.stats_out = stats_out;
   return gemm(st, dt, patches, c->Kp, c->patch_w, c->Kp, x_out, D, M, D, c->Kp, e);
 }
 
@@ -328,10 +377,12 @@ int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int 
   if (b.overflow) { set_error("workspace too small"); return SF_ERR_WORKSPACE; }
   // the im2col operand aliases the (not yet used) MLP buffer: Kp <= I is checked at create time
   void* cur = hidden_states ? hidden_states[0] : x;
-  SF_CHECK(run_embed(c, st, pixels, pix_dtype, B, T, Hh, Ww, time_off, time_total, cur, w.mlp));
+  SF_CHECK(run_embed(c, st, pixels, pix_dtype, B, T, Hh, Ww, time_off, time_total, cur, w.mlp, w.stats[2]));
+  const int parts_d = gemm_stats_parts(static_cast<int>(M), D);
   for (int l = 0; l < c->L; ++l) {
     void* nxt = hidden_states ? hidden_states[l + 1] : cur;
-    SF_CHECK(run_layer(c, st, l, cur, nxt, B, T, S, kv, attentions ? static_cast<float*>(attentions[l]) : nullptr, w));
+    SF_CHECK(run_layer(c, st, l, cur, nxt, B, T, S, kv, attentions ? static_cast<float*>(attentions[l]) : nullptr, w,
+                       w.stats[2], parts_d, w.stats[2]));
     cur = nxt;
   }
   if (kv) kv->seen += T;
@@ -341,8 +392,8 @@ int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int 
   if (pooler) {
     // head scratch aliases the layer scratch (all layers are done)
     Bump hb;
-    hb.base = static_cast<uint8_t*>(w.ln);
-    hb.size = static_cast<uint8_t*>(ws) + ws_bytes - static_cast<uint8_t*>(w.ln);
+    hb.base = static_cast<uint8_t*>(w.qkv);
+    hb.size = static_cast<uint8_t*>(ws) + ws_bytes - static_cast<uint8_t*>(w.qkv);
     SF_CHECK(run_head(c, st, last_hidden, B * T, S, pooler, hb));
   }
   return 0;
@@ -399,19 +450,18 @@ struct Binder {
     if (static_cast<size_t>(n) > scratch_elems) { set_error("bind scratch too small"); return SF_ERR_INVALID; }
     return cast(st, d->dtype, d->data, kF32, scratch[slot], n);
   }
-  // W (+ lora_b . lora_a) in activation dtype
-  int mat_lora(const std::string& wname, const std::string& aname, const std::string& bname, long O, long I,
-               void** out) {
-    const sf_weight_desc* a = find(aname, false);
-    const sf_weight_desc* bm = find(bname, false);
-    if (!a || !bm) return mat(wname, O, I, out);
+  // W (+ lora_b . lora_a, …siglip.py:653-654, 749-751) as fp32 in scratch[0]
+  int load_f32(const std::string& wname, const std::string& aname, const std::string& bname, long O, long I) {
     const sf_weight_desc* wd = find(wname);
     if (!wd) return SF_ERR_INVALID;
     SF_CHECK(expect(wd, O * I));
+    SF_CHECK(to_scratch(0, wd, O * I));
+    const sf_weight_desc* a = aname.empty() ? nullptr : find(aname, false);
+    const sf_weight_desc* bm = bname.empty() ? nullptr : find(bname, false);
+    if (!a || !bm) return 0;
     const long R = numel(a) / I;
     SF_CHECK(expect(a, R * I));
     SF_CHECK(expect(bm, O * R));
-    SF_CHECK(to_scratch(0, wd, O * I));
     SF_CHECK(to_scratch(1, a, R * I));
     SF_CHECK(to_scratch(2, bm, O * R));
     const long total = O * I;
@@ -419,15 +469,43 @@ struct Binder {
                                                                                   static_cast<int>(O), static_cast<int>(I),
                                                                                   static_cast<int>(R));
     count_launch();
+    return 0;
+  }
+  // W (+ LoRA) in activation dtype
+  int mat_lora(const std::string& wname, const std::string& aname, const std::string& bname, long O, long I,
+               void** out) {
+    SF_CHECK(load_f32(wname, aname, bname, O, I));
     *out = arena.take(O * I * 2);
+    if (!*out) { set_error("sf_bind_weights: arena exhausted at '%s'", wname.c_str()); return SF_ERR_STATE; }
     return cast(st, kF32, scratch[0], c->cfg.dtype, *out, O * I);
+  }
+  // Linear preceded by a LayerNorm (gamma, beta already in the arena): gamma-scaled matrix, folded
+  // bias and column sums (see ln_fold_kernel)
+  int mat_ln(const std::string& wname, const std::string& aname, const std::string& bname, const std::string& biasname,
+             const float* gamma, const float* beta, long O, long I, void** w_out, float** bias_out, float** colsum_out) {
+    SF_CHECK(load_f32(wname, aname, bname, O, I));
+    float* bias_raw = nullptr;
+    SF_CHECK(vec(biasname, O, &bias_raw));
+    *w_out = arena.take(O * I * 2);
+    *bias_out = static_cast<float*>(arena.take(O * sizeof(float)));
+    *colsum_out = static_cast<float*>(arena.take(O * sizeof(float)));
+    if (!*w_out || !*bias_out || !*colsum_out) { set_error("sf_bind_weights: arena exhausted at '%s'", wname.c_str()); return SF_ERR_STATE; }
+    const unsigned blocks = static_cast<unsigned>((O + 7) / 8);
+    if (c->cfg.dtype == kBF16)
+      ln_fold_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(scratch[0], gamma, beta, bias_raw, static_cast<__nv_bfloat16*>(*w_out),
+                                                            *colsum_out, *bias_out, static_cast<int>(O), static_cast<int>(I));
+    else
+      ln_fold_kernel<__half><<<blocks, 256, 0, st>>>(scratch[0], gamma, beta, bias_raw, static_cast<__half*>(*w_out),
+                                                     *colsum_out, *bias_out, static_cast<int>(O), static_cast<int>(I));
+    count_launch();
+    return 0;
   }
 };
 
 size_t arena_bytes_for(const sf_ctx* c) {
   const size_t D = c->D, I = c->I, L = c->L, K = c->Kp, S0 = c->S0, F = c->cfg.num_frames;
   size_t per_layer = (3 * D * D + D * D * 3 + 3 * D * D + D * D + 2 * D * I) * 2  // matrices (incl. folded)
-                     + (3 * D + D * 3 + 3 * D + D + I + D + 6 * D + 1) * 4 + 40 * 256;
+                     + (3 * D + D * 3 + 3 * D + D + I + D + 6 * D + 1 + 2 * (3 * D + 3 * D + I)) * 4 + 60 * 256;
   size_t other = D * K * 2 + (D + S0 * D + F * D + 2 * D) * 4 + (2 * D * D + D * D + 2 * D * I) * 2 +
                  (2 * D + D + I + D + D + 2 * D) * 4 + 40 * 256;
   return per_layer * L + other + (1 << 20);
@@ -529,8 +607,8 @@ int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
       SF_CHECK(b.vec(p + "layernorm_before.bias", D, &lw.ln_s_b));
       SF_CHECK(b.vec(p + "layernorm_after.weight", D, &lw.ln_a_g));
       SF_CHECK(b.vec(p + "layernorm_after.bias", D, &lw.ln_a_b));
-      SF_CHECK(b.mat(p + "temporal_attention.attention.qkv.weight", 3 * D, D, &lw.t_qkv_w));
-      SF_CHECK(b.vec(p + "temporal_attention.attention.qkv.bias", 3 * D, &lw.t_qkv_b));
+      SF_CHECK(b.mat_ln(p + "temporal_attention.attention.qkv.weight", "", "", p + "temporal_attention.attention.qkv.bias",
+                        lw.ln_t_g, lw.ln_t_b, 3 * D, D, &lw.t_qkv_w, &lw.t_qkv_b, &lw.t_qkv_cs));
       SF_CHECK(b.mat(p + "temporal_attention.output.dense.weight", D, D, &lw.t_out_w));
       SF_CHECK(b.vec(p + "temporal_attention.output.dense.bias", D, &lw.t_out_b));
       SF_CHECK(b.mat(p + "temporal_dense.weight", D, D, &lw.t_dense_w));
@@ -553,14 +631,14 @@ int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
                                                                           static_cast<int>(D), 1.0f);
         count_launch();
       }
-      SF_CHECK(b.mat_lora(p + "attention.attention.qkv.weight", p + "attention.attention.qkv_lora_a.weight",
-                          p + "attention.attention.qkv_lora_b.weight", 3 * D, D, &lw.s_qkv_w));
-      SF_CHECK(b.vec(p + "attention.attention.qkv.bias", 3 * D, &lw.s_qkv_b));
+      SF_CHECK(b.mat_ln(p + "attention.attention.qkv.weight", p + "attention.attention.qkv_lora_a.weight",
+                        p + "attention.attention.qkv_lora_b.weight", p + "attention.attention.qkv.bias", lw.ln_s_g,
+                        lw.ln_s_b, 3 * D, D, &lw.s_qkv_w, &lw.s_qkv_b, &lw.s_qkv_cs));
       SF_CHECK(b.mat_lora(p + "attention.output.dense.weight", p + "attention.output.dense_lora_a.weight",
                           p + "attention.output.dense_lora_b.weight", D, D, &lw.s_out_w));
       SF_CHECK(b.vec(p + "attention.output.dense.bias", D, &lw.s_out_b));
-      SF_CHECK(b.mat(p + "intermediate.dense.weight", I, D, &lw.fc1_w));
-      SF_CHECK(b.vec(p + "intermediate.dense.bias", I, &lw.fc1_b));
+      SF_CHECK(b.mat_ln(p + "intermediate.dense.weight", "", "", p + "intermediate.dense.bias", lw.ln_a_g, lw.ln_a_b, I,
+                        D, &lw.fc1_w, &lw.fc1_b, &lw.fc1_cs));
       SF_CHECK(b.mat(p + "output.dense.weight", D, I, &lw.fc2_w));
       SF_CHECK(b.vec(p + "output.dense.bias", D, &lw.fc2_b));
     }
@@ -690,7 +768,7 @@ int sf_embed_forward(sf_ctx* c, void* stream, const void* pixels, int pixels_dty
   if (b.overflow) { set_error("sf_embed_forward: workspace too small (need %zu)", b.off); return SF_ERR_WORKSPACE; }
   if (time_total < time_off + T) time_total = time_off + T;
   return run_embed(c, static_cast<cudaStream_t>(stream), pixels, pixels_dtype, B, T, Hh, Ww, time_off, time_total, x_out,
-                   patches);
+                   patches, nullptr);
 }
 
 int sf_layer_forward(sf_ctx* c, void* stream, int layer, const void* x_in, void* x_out, int B, int T, int S, sf_kv* kv,
@@ -701,8 +779,13 @@ int sf_layer_forward(sf_ctx* c, void* stream, int layer, const void* x_in, void*
   Bump b;
   b.base = static_cast<uint8_t*>(workspace); b.size = workspace_bytes;
   WsPlan w;
-  SF_CHECK(carve_layer_ws(c, static_cast<long>(B) * T * S, b, w));
-  return run_layer(c, static_cast<cudaStream_t>(stream), layer, x_in, x_out, B, T, S, kv, attn_probs, w);
+  const long M = static_cast<long>(B) * T * S;
+  SF_CHECK(carve_layer_ws(c, M, b, w));
+  // x_in comes from the caller: one pass for its row statistics (inside sf_forward they are a
+  // by-product of the GEMM that wrote the rows)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SF_CHECK(rowstats(st, c->cfg.dtype, x_in, c->D, static_cast<int>(M), c->D, w.stats[2]));
+  return run_layer(c, st, layer, x_in, x_out, B, T, S, kv, attn_probs, w, w.stats[2], 1, w.stats[2]);
 }
 
 int sf_final_norm(sf_ctx* c, void* stream, const void* x, int B, int T, int S, void* last_hidden) {
@@ -730,6 +813,8 @@ int sf_op_gemm(void* stream, int dtype, const void* A, int lda, const void* W, i
     g.row_map = e->row_map; g.T = e->T > 0 ? e->T : 1; g.S = e->S > 0 ? e->S : 1;
     g.pos = e->pos; g.time_emb = e->time_emb; g.time_len = e->time_len; g.time_total = e->time_total;
     g.time_off = e->time_off;
+    g.ln_stats = static_cast<const float2*>(e->ln_stats); g.ln_parts = e->ln_parts; g.ln_colsum = e->ln_colsum;
+    g.ln_eps = e->ln_eps; g.stats_out = static_cast<float2*>(e->stats_out);
   }
   return gemm(static_cast<cudaStream_t>(stream), dtype, A, lda, W, ldw, out, ldo, M, N, K, g);
 }
@@ -753,10 +838,14 @@ int sf_op_kv_append(void* stream, int dtype, const void* qkv, int ld_qkv, void* 
   return kv_append(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, kcache, vcache, Tcap, sites, heads, Tq, pos0);
 }
 int sf_op_spatial_attention(void* stream, int dtype, const void* qkv, int ld_qkv, void* out, int ld_out, int frames,
-                            int heads, int S, float scale, float* probs) {
-  return spatial_attention(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, out, ld_out, frames, heads, S, scale,
-                           probs);
+                            int heads, int S, int T_inner, float scale, float* probs) {
+  return spatial_attention(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, out, ld_out, frames, heads, S, T_inner,
+                           scale, probs);
 }
+int sf_op_rowstats(void* stream, int dtype, const void* x, int ldx, int M, int D, void* stats) {
+  return rowstats(static_cast<cudaStream_t>(stream), dtype, x, ldx, M, D, static_cast<float2*>(stats));
+}
+int sf_op_gemm_stats_parts(int M, int N) { return gemm_stats_parts(M, N); }
 int sf_op_pool_attention(void* stream, int dtype, const void* kv, int ld_kv, const float* q, void* out, int ld_out,
                          int frames, int heads, int S) {
   return pool_attention(static_cast<cudaStream_t>(stream), dtype, kv, ld_kv, q, out, ld_out, frames, heads, S);

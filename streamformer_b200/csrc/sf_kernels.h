@@ -34,6 +34,17 @@ struct GemmEpilogue {
   int time_len = 0;                 // rows in the time table (config.num_frames)
   int time_total = 0;               // total frames the table is stretched over (>= time_off+T)
   int time_off = 0;                 // frames already seen (streaming)
+  // LayerNorm folded into this GEMM: A holds the RAW rows x, W was pre-scaled by gamma at bind
+  // time, bias is b + W.beta, and the epilogue finishes the normalisation per row:
+  //   v = rstd[m] * (acc - mean[m] * ln_colsum[n]) + bias[n]
+  // with mean/rstd from the partial (sum, sum of squares) of row m written by the producer of x.
+  const float2* ln_stats = nullptr; // [ln_parts][M]
+  int ln_parts = 0;
+  const float* ln_colsum = nullptr; // [N] fp32: sum_k W'[n,k] of the packed (rounded) matrix
+  float ln_eps = 0.f;
+  // Partial row statistics of the OUTPUT rows (values as rounded to the activation dtype), one
+  // (sum, sumsq) per row and column group, for the next folded LayerNorm: [gemm_stats_parts(M,N)][M]
+  float2* stats_out = nullptr;
 };
 
 // C[M,N] = A[M,K] . W[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
@@ -41,6 +52,15 @@ struct GemmEpilogue {
 // Requirements: K % 8 == 0, N % 8 == 0, lda/ldw/ldo/ldr % 8 == 0, 16-byte aligned pointers.
 int gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out,
          int ldo, int M, int N, int K, const GemmEpilogue& epi);
+
+// Number of column groups (partials per row) gemm() writes to GemmEpilogue::stats_out for an M x N output.
+int gemm_stats_parts(int M, int N);
+// Upper bound of gemm_stats_parts over all tile shapes (columns per partial >= 64).
+inline int gemm_stats_parts_max(int N) { return (N + 63) / 64; }
+
+// stats[m] = (sum_d x[m,d], sum_d x[m,d]^2): a one-partial row-statistics table for rows that were
+// not produced by gemm() (block-level API entry points).
+int rowstats(cudaStream_t stream, int dtype, const void* x, int ldx, int M, int D, float2* stats);
 
 // y = LayerNorm(x) * gamma + beta over the last dim D (fp32 statistics, biased variance).
 // row_map as in GemmEpilogue (input row m -> output row r), T/S for the decomposition.
@@ -67,11 +87,14 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
 int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
               int Tcap, int sites, int heads, int Tq, int pos0);
 
-// Spatial attention inside each frame: qkv rows (frame*S + n), q|k|v column blocks of width
-// heads*64; full (non-causal) softmax over the S keys; out rows (frame*S + n).
+// Spatial attention inside each frame: q|k|v column blocks of width heads*64; full (non-causal)
+// softmax over the S keys of the frame.  Row of token n of frame f (same for qkv and out):
+//   T_inner <= 1 : f*S + n                      (frames contiguous, (b,t,n) order)
+//   T_inner  > 1 : (b*S + n)*T_inner + t, f = b*T_inner + t   (the residual stream's (b,n,t) order:
+//                  the frame is read in place with a row stride of T_inner, no permute copy)
 // probs (optional, fp32 [frames, heads, S, S]) receives the attention probabilities.
 int spatial_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* out,
-                      int ld_out, int frames, int heads, int S, float scale, float* probs);
+                      int ld_out, int frames, int heads, int S, int T_inner, float scale, float* probs);
 
 // Attention-pooling core of the SigLIP head: for each frame and head, softmax_n(q_h . K[n,h]) V[n,h].
 //   kv rows (frame*S + n): [K (heads*64) | V (heads*64)], q: [heads*64] fp32 (already scaled).
@@ -101,6 +124,14 @@ struct ProfScope {
     if (on) prof_begin(st, cls, flops, bytes);
   }
   ~ProfScope() { if (on) prof_end(st); }
+};
+
+// Launch configuration carrying the library-wide attributes: programmatic stream serialization
+// (PDL; SF_PDL=0 disables it) and, optionally, a CTA-cluster dimension.
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster = 1);
 };
 
 const char* last_error();

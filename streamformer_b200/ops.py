@@ -38,9 +38,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
          row_map: int = N.SF_ROW_IDENTITY, T: int = 1, S: int = 1, pos: Optional[torch.Tensor] = None,
          time_emb: Optional[torch.Tensor] = None, time_total: int = 0, time_off: int = 0,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[r] = epilogue(a[m] @ w.T); a [M,K], w [N,K] (nn.Linear layout), fp32 bias/pos/time/gate."""
-    _req(a, w, bias, residual, gate, pos, time_emb, out)
+         out: Optional[torch.Tensor] = None, ln_stats: Optional[torch.Tensor] = None,
+         ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 0.0,
+         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = epilogue(a[m] @ w.T); a [M,K], w [N,K] (nn.Linear layout), fp32 bias/pos/time/gate.
+    ln_stats [parts, M, 2] + ln_colsum [N]: LayerNorm folded into the GEMM (w pre-scaled by gamma).
+    stats_out [gemm_stats_parts(M, N), M, 2]: partial row statistics of the output."""
+    _req(a, w, bias, residual, gate, pos, time_emb, out, ln_stats, ln_colsum, stats_out)
     M, K = a.shape
     Nn = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
@@ -53,7 +57,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     e.pos = _p(pos); e.time_emb = _p(time_emb)
     e.time_len = time_emb.shape[0] if time_emb is not None else 0
     e.time_total = time_total; e.time_off = time_off
-    for t in (bias, gate, pos, time_emb):
+    e.ln_stats = _p(ln_stats); e.ln_parts = ln_stats.shape[0] if ln_stats is not None else 0
+    e.ln_colsum = _p(ln_colsum); e.ln_eps = ln_eps; e.stats_out = _p(stats_out)
+    for t in (bias, gate, pos, time_emb, ln_stats, ln_colsum, stats_out):
         assert t is None or t.dtype == torch.float32
     N.check(N.load().sf_op_gemm(_stream(), sf_dtype(a.dtype), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
                                 out.data_ptr(), out.stride(0), M, Nn, K, e), "sf_op_gemm")
@@ -102,14 +108,29 @@ def kv_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, sit
                                      vcache.data_ptr(), kcache.shape[2], sites, heads, Tq, pos0), "sf_op_kv_append")
 
 
+def gemm_stats_parts(M: int, Nn: int) -> int:
+    return int(N.load().sf_op_gemm_stats_parts(M, Nn))
+
+
+def rowstats(x: torch.Tensor) -> torch.Tensor:
+    """[1, M, 2] fp32 (sum, sum of squares) per row."""
+    _req(x)
+    M, D = x.shape
+    st = torch.empty(1, M, 2, dtype=torch.float32, device=x.device)
+    N.check(N.load().sf_op_rowstats(_stream(), sf_dtype(x.dtype), x.data_ptr(), x.stride(0), M, D, st.data_ptr()),
+            "sf_op_rowstats")
+    return st
+
+
 def spatial_attention(qkv: torch.Tensor, frames: int, heads: int, S: int, scale: float,
-                      want_probs: bool = False):
+                      want_probs: bool = False, T_inner: int = 1):
     _req(qkv)
     D = heads * 64
     out = torch.empty(frames * S, D, dtype=qkv.dtype, device=qkv.device)
     probs = torch.empty(frames, heads, S, S, dtype=torch.float32, device=qkv.device) if want_probs else None
     N.check(N.load().sf_op_spatial_attention(_stream(), sf_dtype(qkv.dtype), qkv.data_ptr(), qkv.stride(0),
-                                             out.data_ptr(), out.stride(0), frames, heads, S, scale, _p(probs)),
+                                             out.data_ptr(), out.stride(0), frames, heads, S, T_inner, scale,
+                                             _p(probs)),
             "sf_op_spatial_attention")
     return (out, probs) if want_probs else out
 

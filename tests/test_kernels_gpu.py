@@ -83,6 +83,97 @@ def test_gemm_gated_residual_inplace():
     _close(out, ref, torch.bfloat16, "gemm+gated residual")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,act", [(3136, 2304, 768, 0), (25088, 3072, 768, 1), (300, 768, 768, 0), (784, 2304, 768, 0),
+                                       (1000, 3072, 768, 2)])
+def test_gemm_folded_layernorm(dtype, M, N, K, act):
+    """LayerNorm folded into the projection: A holds the raw rows (large mean, wide spread), W is
+    pre-scaled by gamma, the epilogue applies rstd * (acc - mean * colsum) + (b + W.beta).  The row
+    statistics come from ops.rowstats (one partial) — reference is LN in fp32 followed by the Linear."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(21 + M + N)
+    x = (torch.randn(M, K, generator=g) * (0.5 + 3 * torch.rand(M, 1, generator=g)) + 2 * torch.randn(M, 1, generator=g))
+    x[:, 7] += 20.0  # a massive-activation channel as ViT residual streams have
+    x = x.to(DEV, dtype)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    gamma = (1 + 0.3 * torch.randn(K, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(K, generator=g)).to(DEV)
+    wp = (w * gamma).to(dtype)
+    colsum = wp.float().sum(1)
+    biasp = bias + w @ beta
+    stats = ops.rowstats(x)
+    out = ops.gemm(x, wp, bias=biasp, act=act, ln_stats=stats, ln_colsum=colsum, ln_eps=1e-6)
+    ref = torch.nn.functional.layer_norm(x.float(), (K,), gamma, beta, 1e-6) @ w.t() + bias
+    if act:
+        ref = torch.nn.functional.gelu(ref, approximate="none" if act == 1 else "tanh")
+    _close(out, ref, dtype, f"gemm+folded LN {M}x{N}x{K} act={act}", scale=2.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(25088, 768, 768), (3136, 768, 3072), (784, 768, 768), (300, 768, 768)])
+def test_gemm_stats_out_feeds_folded_layernorm(M, N, K):
+    """A residual-epilogue GEMM writes partial (sum, sumsq) of its output rows; they must equal the
+    statistics of the stored (rounded) rows, and drive the next GEMM's folded LayerNorm."""
+    ops = _ops()
+    dtype = torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(31 + M)
+    a = torch.randn(M, K, generator=g).to(DEV, dtype)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DEV, dtype)
+    res = (torch.randn(M, N, generator=g) * 2 + 1).to(DEV, dtype)
+    bias = torch.randn(N, generator=g).to(DEV)
+    parts = ops.gemm_stats_parts(M, N)
+    stats = torch.full((parts, M, 2), float("nan"), device=DEV)
+    y = ops.gemm(a, w, bias=bias, residual=res, stats_out=stats)
+    tot = stats.sum(0)
+    yf = y.float()
+    assert torch.allclose(tot[:, 0], yf.sum(1), rtol=1e-4, atol=1e-2), (tot[:, 0] - yf.sum(1)).abs().max()
+    assert torch.allclose(tot[:, 1], yf.pow(2).sum(1), rtol=1e-4, atol=1e-2)
+    # consumer
+    N2 = 2304
+    w2 = (torch.randn(N2, N, generator=g) * 0.05).to(DEV)
+    gamma = (1 + 0.3 * torch.randn(N, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(N, generator=g)).to(DEV)
+    wp = (w2 * gamma).to(dtype)
+    out = ops.gemm(y, wp, bias=w2 @ beta, ln_stats=stats, ln_colsum=wp.float().sum(1), ln_eps=1e-6)
+    ref = torch.nn.functional.layer_norm(yf, (N,), gamma, beta, 1e-6) @ w2.t()
+    _close(out, ref, dtype, "stats_out -> folded LN", scale=2.0)
+
+
+def test_gemm_embed_stats_out():
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(41)
+    B, T, S, K, N = 2, 4, 196, 768, 768
+    M = B * T * S
+    a = torch.randn(M, K, generator=g).to(DEV, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DEV, torch.bfloat16)
+    pos = torch.randn(S, N, generator=g).to(DEV)
+    time = torch.randn(16, N, generator=g).to(DEV)
+    stats = torch.zeros(ops.gemm_stats_parts(M, N), M, 2, device=DEV)
+    y = ops.gemm(a, w, row_map=1, T=T, S=S, pos=pos, time_emb=time, time_total=T, stats_out=stats).float()
+    tot = stats.sum(0)
+    assert torch.allclose(tot[:, 0], y.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[:, 1], y.pow(2).sum(1), rtol=1e-4, atol=1e-2)
+
+
+def test_gelu_erf_epilogue_accuracy():
+    """The x*sigmoid(poly) form of the erf GELU stays within the bf16 output rounding of the exact one."""
+    ops = _ops()
+    K, N, M = 64, 256, 4096
+    a = torch.zeros(M, K, device=DEV, dtype=torch.float16)
+    a[:, 0] = 1.0
+    w = torch.zeros(N, K, device=DEV, dtype=torch.float16)
+    xs = torch.linspace(-9, 9, M * N, device=DEV).view(M, N)
+    bias = xs[0].clone()          # per-column offsets ...
+    a[:, 1] = (xs[:, 0] - xs[0, 0]).to(torch.float16)   # ... plus a per-row shift through the GEMM
+    w[:, 1] = 1.0
+    pre = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias=bias, act=1).float()
+    ref = torch.nn.functional.gelu(pre.double(), approximate="none")
+    err = (out.double() - ref).abs()
+    bound = ref.abs() * 2.0 ** -10 + 4e-5     # fp16 rounding (2^-11) + the fit's 1.8e-4 relative / 3.5e-5 absolute error
+    assert bool((err <= bound).all()), (err - bound).max()
+
+
 @pytest.mark.parametrize("B,T,S", [(2, 16, 196), (1, 6, 196), (3, 5, 49)])
 def test_gemm_row_maps(B, T, S):
     """QKV projection writes (b,t,n) rows from (b,n,t) input; out-proj maps back with residual."""
@@ -223,6 +314,22 @@ def test_spatial_attention(dtype, frames, S):
     _close(out, ref, dtype, "spatial attention", scale=2.0)
     pref = ((x[0] @ x[1].transpose(-2, -1)) * 0.125).softmax(-1)
     assert torch.allclose(probs, pref, atol=1e-4, rtol=1e-3), (probs - pref).abs().max()
+
+
+@pytest.mark.parametrize("B,T,S", [(2, 16, 196), (1, 6, 196), (3, 5, 49), (4, 1, 196), (1, 24, 64)])
+def test_spatial_attention_in_place_layout(B, T, S):
+    """Frames read in place from the residual stream's (b,n,t) row order (row stride T), outputs
+    written back in the same order: must equal the contiguous-frame result on permuted rows."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(18)
+    H, D = 12, 768
+    qkv_bnt = torch.randn(B * S * T, 3 * D, generator=g).to(DEV, torch.bfloat16)
+    out, probs = ops.spatial_attention(qkv_bnt, B * T, H, S, 0.125, want_probs=True, T_inner=T)
+    qkv_btn = qkv_bnt.view(B, S, T, 3 * D).permute(0, 2, 1, 3).reshape(B * T * S, 3 * D).contiguous()
+    ref, pref = ops.spatial_attention(qkv_btn, B * T, H, S, 0.125, want_probs=True)
+    ref_bnt = ref.view(B, T, S, D).permute(0, 2, 1, 3).reshape(B * S * T, D)
+    assert torch.equal(out, ref_bnt)
+    assert torch.equal(probs, pref)
 
 
 @pytest.mark.parametrize("frames,S", [(16, 196), (5, 49), (1, 400)])

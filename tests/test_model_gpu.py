@@ -228,7 +228,13 @@ def test_block_level_api_matches_forward():
         assert torch.equal(x, full.hidden_states[0])
         for i, blk in enumerate(model.encoder.layer):
             x = blk(x, 4, output_attentions=False)[0]
-            assert torch.equal(x, full.hidden_states[i + 1])
+            # same kernels; only the LayerNorm row statistics of the block's input are summed in a
+            # different order (one rowstats pass here, GEMM-epilogue partials inside forward), so
+            # some outputs round to the neighbouring bf16 value (and layer 2 starts from those)
+            ref = full.hidden_states[i + 1].float()
+            diff = (x.float() - ref).abs()
+            assert float(diff.max()) <= 2.0 ** -6 * float(ref.abs().max())
+            assert float(diff.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()) <= 2.0 ** -9
         pooled = model.head(full.last_hidden_state.reshape(8, 196, 768))
     assert torch.equal(pooled.reshape(2, 4, 768), full.pooler_output)
 

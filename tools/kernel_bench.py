@@ -56,26 +56,35 @@ def main():
         if kw.get("residual"):
             extra["residual_list"] = [torch.randn(M, Nn, device=dev, dtype=dt) for _ in range(nrot)]
         gate = torch.tensor([0.5], device=dev) if kw.get("gate") else None
+        ln_stats = ops.rowstats(As[0]).repeat(6, 1, 1).contiguous() if kw.get("ln") else None
+        ln_colsum = torch.randn(Nn, device=dev) if kw.get("ln") else None
+        stats_out = torch.empty(ops.gemm_stats_parts(M, Nn), M, 2, device=dev) if kw.get("stats") else None
 
         def fn(i):
             ops.gemm(As[i], Ws[i], bias=bias, act=kw.get("act", 0),
                      residual=extra["residual_list"][i] if "residual_list" in extra else None, gate=gate,
-                     row_map=kw.get("row_map", 0), T=a.T, S=S, out=outs[i])
+                     row_map=kw.get("row_map", 0), T=a.T, S=S, out=outs[i], ln_stats=ln_stats, ln_colsum=ln_colsum,
+                     ln_eps=1e-6, stats_out=stats_out)
         ms = timeit(fn, nrot)
         tf = 2.0 * M * Nn * K / (ms * 1e-3) / 1e12
         res[name] = {"ms": round(ms, 4), "tflops": round(tf, 1)}
         print(f"{name:28s} M={M} N={Nn} K={K}: {ms*1e3:8.1f} us  {tf:7.1f} TFLOP/s", flush=True)
 
+    if a.only and "epi" in a.only:
+        gemm_case("qkv (folded LN)", 3 * D, D, ln=True)
+        gemm_case("proj (bias)", D, D)
+        gemm_case("fc1 (folded LN+gelu)", I, D, act=1, ln=True)
     if not a.only or "gemm" in a.only:
         gemm_case("qkv (bias)", 3 * D, D)
-        gemm_case("qkv (bias, BNT->BTN)", 3 * D, D, row_map=2)
+        gemm_case("qkv (folded LN)", 3 * D, D, ln=True)
         gemm_case("proj (bias)", D, D)
         gemm_case("proj (bias+res)", D, D, residual=True)
-        gemm_case("proj (bias+res+gate)", D, D, residual=True, gate=True)
-        gemm_case("proj (bias+res, BTN->BNT)", D, D, residual=True, row_map=1)
+        gemm_case("proj (bias+res+gate+stats)", D, D, residual=True, gate=True, stats=True)
         gemm_case("fc1 (bias)", I, D)
         gemm_case("fc1 (bias+gelu)", I, D, act=1)
+        gemm_case("fc1 (folded LN+gelu)", I, D, act=1, ln=True)
         gemm_case("fc2 (bias+res)", D, I, residual=True)
+        gemm_case("fc2 (bias+res+stats)", D, I, residual=True, stats=True)
         gemm_case("head kv (bias)", 2 * D, D)
 
     if a.only and "cublas" in a.only:
@@ -104,7 +113,7 @@ def main():
 
     if not a.only or "attn" in a.only:
         qs = [torch.randn(M, 3 * D, device=dev, dtype=dt) for _ in range(nrot)]
-        ms = timeit(lambda i: ops.spatial_attention(qs[i], a.B * a.T, 12, S, 0.125), nrot)
+        ms = timeit(lambda i: ops.spatial_attention(qs[i], a.B * a.T, 12, S, 0.125, T_inner=a.T), nrot)
         fl = 4.0 * a.B * a.T * 12 * S * S * 64
         res["spatial_attention"] = {"ms": round(ms, 4), "tflops": round(fl / (ms * 1e-3) / 1e12, 1),
                                     "gbs": round(8.0 * M * D / (ms * 1e-3) / 1e9, 1)}
