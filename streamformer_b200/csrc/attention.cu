@@ -10,6 +10,7 @@
 // These contractions are 3 % of the encoder FLOPs and HBM/L2-bound stand-alone, so they read
 // Q/K/V in place (128-byte head rows, no permute copies) and never materialise the score tensor.
 #include <math.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -527,15 +528,20 @@ int spatial_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qk
   a.qblocks = (S + kSWarps * 16 - 1) / (kSWarps * 16);
   a.scale_log2 = scale * kLog2e;
   const long blocks = static_cast<long>(frames) * heads * a.qblocks;
-  {
+  static const bool use_tc = [] { const char* e = getenv("SF_SPATIAL_TC"); return !(e && e[0] == '0'); }();
+  if (use_tc && spatial_attention_tc_supported(ld_qkv, S)) {
+    int rc = spatial_attention_tc(stream, dtype, qkv, ld_qkv, out, ld_out, frames, heads, S, T_inner, scale);
+    if (rc) return rc;
+  } else {
     ProfScope ps(stream, kProfSpatialAttn, 4.0 * frames * heads * static_cast<double>(S) * S * kHd,
                  2.0 * frames * heads * kHd * 4.0 * S);
     LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(kSWarps * 32), 0, stream);
     if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, spatial_attn_kernel<__nv_bfloat16>, a);
     else cudaLaunchKernelEx(&lc.cfg, spatial_attn_kernel<__half>, a);
+    int rc = check_launch("spatial_attention");
+    if (rc) return rc;
   }
-  int rc = check_launch("spatial_attention");
-  if (rc || !probs) return rc;
+  if (!probs) return 0;
   const long rows = static_cast<long>(frames) * heads * S;
   const long pb = (rows + 3) / 4;
   LaunchCfg lp(dim3(static_cast<unsigned>(pb)), dim3(128), 0, stream);

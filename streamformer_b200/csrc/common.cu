@@ -8,6 +8,7 @@
 
 #include "sf_kernels.h"
 #include "sf_ptx.cuh"
+#include "sf_tma.h"
 
 namespace sf {
 
@@ -57,6 +58,31 @@ int prof_collect(double* ms, double* flops, double* bytes, long long* launches, 
   return 0;
 }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(err));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 
 LaunchCfg::LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster) {
   static const bool pdl = [] { const char* e = getenv("SF_PDL"); return !(e && e[0] == '0'); }();

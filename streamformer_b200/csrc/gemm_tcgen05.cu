@@ -21,6 +21,7 @@
 
 #include "sf_kernels.h"
 #include "sf_ptx.cuh"
+#include "sf_tma.h"
 
 namespace sf {
 
@@ -581,25 +582,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* ptr = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-  if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
-    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(err));
-    return nullptr;
-  }
-  fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  return fn;
-}
-
 // 2D K-major operand map: dims {K, rows}, box {64, box_rows}, 128B swizzle, zero OOB fill.
 int make_operand_map(CUtensorMap* map, int dtype, const void* base, int rows, int K, int ld,
                      int box_rows) {
@@ -620,17 +602,6 @@ int make_operand_map(CUtensorMap* map, int dtype, const void* base, int rows, in
     return -3;
   }
   return 0;
-}
-
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
 }
 
 template <typename T, int BN, int CG, int EPI, int EW>

@@ -96,6 +96,12 @@ int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void*
 int spatial_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* out,
                       int ld_out, int frames, int heads, int S, int T_inner, float scale, float* probs);
 
+// tcgen05 implementation of spatial_attention (attention_tc.cu) for frames of up to 208 tokens;
+// spatial_attention() dispatches to it when supported (SF_SPATIAL_TC=0 forces the mma.sync kernel).
+bool spatial_attention_tc_supported(int ld_qkv, int S);
+int spatial_attention_tc(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* out, int ld_out,
+                         int frames, int heads, int S, int T_inner, float scale);
+
 // Attention-pooling core of the SigLIP head: for each frame and head, softmax_n(q_h . K[n,h]) V[n,h].
 //   kv rows (frame*S + n): [K (heads*64) | V (heads*64)], q: [heads*64] fp32 (already scaled).
 //   out [frames, heads*64] in act dtype.

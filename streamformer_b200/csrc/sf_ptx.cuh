@@ -112,6 +112,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0,
                                              int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -164,6 +173,20 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M x 16 elements per instruction, two 16-bit
+// values per 32-bit column) is read from tensor memory — attention's P matrix never touches smem.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has retired.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -196,6 +219,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 8 consecutive 32-bit columns <- 8 registers per thread
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -212,11 +245,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B   [61,64)
   return d;
 }
-// Instruction descriptor for kind::f16: fp32 accumulate, A and B both K-major.
+// MN-major operand tile, SWIZZLE_128B: rows are K indices, each row holds 64 contiguous 16-bit
+// elements along the operand's M/N dimension (exactly what a TMA box of 64 columns x R rows writes).
+// 8-row groups are 1024 B apart (SBO); a single 64-element atom along MN, so LBO is unused.  One
+// UMMA (K = 16) consumes two 8-row groups: advance the start address by 2048 B per K step.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr) {
+  return umma_desc_sw128_kmajor(smem_addr);   // same field values; the major-ness lives in the instruction descriptor
+}
+// Instruction descriptor for kind::f16: fp32 accumulate, A K-major, B K-major (b_mn = 0) or MN-major (1).
 // ab_fmt: 0 = fp16, 1 = bf16.
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int ab_fmt) {
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int ab_fmt, int b_mn = 0) {
   return (1u << 4) | (static_cast<uint32_t>(ab_fmt) << 7) | (static_cast<uint32_t>(ab_fmt) << 10) |
-         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+         (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
