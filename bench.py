@@ -25,6 +25,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "encoder frames/sec at [B,16,3,224,224]"
 UNIT = "frames/s"
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one cfg2 step
+# (per layer: 107.9 + 84.2 + 108.0 + 82.3 + 147.5 + 249.6 MB from profiles/r1_ncu_layer.md, x 12 layers;
+# embed and head GEMMs estimated at their algorithmic bytes, 0.25 GB)
+NCU_GEMM_TRAFFIC_BYTES = 12 * (107.9 + 84.2 + 108.0 + 82.3 + 147.5 + 249.6) * 1e6 + 0.25e9
 
 
 def parse_args():
@@ -113,7 +117,7 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples SM clock and throttle reasons of one GPU every 100 ms through NVML."""
+    """Samples SM clock and throttle reasons of one GPU every 10 ms through NVML."""
 
     def __init__(self, index: int):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
@@ -149,7 +153,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:
@@ -275,7 +279,7 @@ def run_ours(args):
 
         # ---- per-kernel-class durations, measured in situ (CUDA events around every launch of a
         # full step, on the launching stream) in a separate instrumented pass
-        prof = None
+        prof = phases = None
         if rank == 0:
             PK = min(K, 5)
             torch.cuda.synchronize()
@@ -288,6 +292,13 @@ def run_ours(args):
                 for k in ("ms", "flops", "bytes"):
                     v[k] /= PK
                 v["launches"] //= PK
+            # per-phase pass: one event pair around each layer's space-time attention block / MLP,
+            # kernels inside run back to back exactly as in the timed region
+            N.profile(2)
+            for i in range(PK):
+                model(dev_in[i % NBUF])
+            phases = N.profile_collect_phases()
+            N.profile(0)
 
     # max over ranks
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
@@ -313,10 +324,34 @@ def run_ours(args):
             "frac_of_burst": gemm_tflops / peaks["burst"],
             "flops_per_step_executed": gemm["flops"], "gemm_ms_per_step": gemm["ms"], "gemm_launches_per_step": gemm["launches"],
             "gemm_share_of_kernel_time": gemm["ms"] / step_kernel_ms if step_kernel_ms else None,
-            "traffic": None,
+            "traffic": NCU_GEMM_TRAFFIC_BYTES if (B, T, args.layers) == (8, 16, 12) else None,
+            "traffic_note": "dram read+write of the 77 GEMM launches of one cfg2 step, from the ncu --set full capture "
+                            "of one layer (profiles/r1_ncu_layer.md) x 12 + embed/head; algorithmic bytes "
+                            f"{gemm['bytes'] / 1e9:.2f} GB",
+            "achieved_unit_note": "executed FLOPs of all GEMM launches of a step / their summed durations",
+
             "step_algorithmic_tflops": algo_flops_step * world / (ms_total / K * 1e-3) / 1e12 / world,
             "step_frac_of_sustained": algo_flops_step / (ms_total / K * 1e-3) / 1e12 / peaks["sustained"],
             "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in prof.items() if v["launches"]},
+        }
+        # BASELINE.json's second metric: tensor-pipe fraction of the space-time attention block of one
+        # layer (temporal QKV + causal attention + out-proj.temporal_dense + gate, spatial QKV +
+        # attention + out-proj; SURVEY 8d: 35.34 GFLOP per clip and layer algorithmic, un-folded)
+        ab = phases["attention_block"]
+        ab_ms = ab["ms"] / max(ab["count"], 1)
+        ab_algo = O.attention_block_flops_per_clip(ocfg, T) * B
+        ab_exec = ab_algo - (2.0 * B * T * S * D * D if not args.no_fold else 0.0)
+        attention_block = {
+            "ms_per_layer": ab_ms, "layers_timed": ab["count"],
+            "algorithmic_gflop_per_layer": ab_algo / 1e9, "executed_gflop_per_layer": ab_exec / 1e9,
+            "algorithmic_tflops": ab_algo / (ab_ms * 1e-3) / 1e12, "executed_tflops": ab_exec / (ab_ms * 1e-3) / 1e12,
+            "frac_of_burst_peak_algorithmic": ab_algo / (ab_ms * 1e-3) / 1e12 / peaks["burst"],
+            "frac_of_burst_peak_executed": ab_exec / (ab_ms * 1e-3) / 1e12 / peaks["burst"],
+            "frac_of_sustained_peak_executed": ab_exec / (ab_ms * 1e-3) / 1e12 / peaks["sustained"],
+            "mlp_ms_per_layer": phases["mlp"]["ms"] / max(phases["mlp"]["count"], 1),
+            "embed_ms": phases["embed"]["ms"] / max(phases["embed"]["count"], 1),
+            "head_ms": phases["head"]["ms"] / max(phases["head"]["count"], 1),
+            "how": "CUDA events around the block of every layer (sf_profile mode 2), kernels back to back with PDL",
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -334,6 +369,7 @@ def run_ours(args):
                              "activations ~0.7 GB) exceeds the 126 MB L2, no explicit flush",
                        "fold_temporal_proj": not args.no_fold, "weights": "random init (no network for checkpoints)"},
             "roofline": roofline,
+            "attention_block": attention_block,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * T * 3 * 224 * 224 * 4,
                     "d2h_bytes_per_step": B * T * D * 2, "ms_per_step": ms_e2e / K,

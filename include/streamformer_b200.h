@@ -83,8 +83,15 @@ uint64_t sf_launch_count(void);
  * 2 im2col, 3 temporal attention, 4 spatial attention, 5 pooling attention, 6 kv append, 7 other),
  * the summed duration [ms], executed FLOPs, algorithmic bytes and launch count since the last call. */
 #define SF_PROFILE_CLASSES 8
-int sf_profile(int enable);
+int sf_profile(int mode);   /* 0 off, 1 per-kernel events, 2 per-phase events */
 int sf_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int n_classes);
+/* Phase timing (mode 2): one event pair around each phase of sf_forward, the kernels inside run back
+ * to back as in production.  Phases: 0 embedding (im2col + patch GEMM), 1 space-time attention block
+ * of a layer (temporal QKV, temporal attention, out-proj.temporal_dense + gate, spatial QKV, spatial
+ * attention, out-proj), 2 MLP of a layer, 3 post-LN + pooling head.  ms / count are summed since the
+ * last call (count = number of phase instances, e.g. layers). */
+#define SF_PROFILE_PHASES 4
+int sf_profile_collect_phases(double* ms, long long* count, int n_phases);
 
 /* ---- model lifetime ---------------------------------------------------------------------- */
 /* replaces TimesformerMultiTaskingModelSigLIP.__init__ (…siglip.py:1244-1258) */

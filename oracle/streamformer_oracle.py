@@ -370,6 +370,15 @@ def forward(w, cfg: OracleConfig, pixels: np.ndarray, output_hidden_states: bool
 
 
 # --------------------------------------------------------------------------------------- accounting
+def attention_block_flops_per_clip(cfg: OracleConfig, T: int) -> float:
+    """Algorithmic FLOPs of ONE layer's space-time attention block for one clip (SURVEY.md 8d:
+    temporal QKV + attention + out-proj + temporal_dense, spatial QKV + attention + out-proj; 35.34 G
+    at T=16)."""
+    D, N = cfg.hidden_size, cfg.num_patches
+    M = T * N
+    return float(2 * M * D * 3 * D * 2 + 2 * M * D * D * 3 + 2 * 2 * M * T * D + 2 * 2 * M * N * D)
+
+
 def flops_per_clip(cfg: OracleConfig, T: int) -> float:
     """Algorithmic FLOPs (2*M*N*K, full non-causal attention count, no LoRA, un-folded graph) of one
     clip of T frames — the figure BASELINE.md §4 and bench.py's roofline use."""

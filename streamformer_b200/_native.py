@@ -19,7 +19,7 @@ SF_ROW_IDENTITY, SF_ROW_BTN_TO_BNT, SF_ROW_BNT_TO_BTN = 0, 1, 2
 
 # every symbol include/streamformer_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
-    "sf_last_error", "sf_version", "sf_launch_count", "sf_profile", "sf_profile_collect",
+    "sf_last_error", "sf_version", "sf_launch_count", "sf_profile", "sf_profile_collect", "sf_profile_collect_phases",
     "sf_create", "sf_destroy", "sf_bind_weights", "sf_set_pos_embed",
     "sf_workspace_bytes", "sf_forward",
     "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_forward_stream",
@@ -80,6 +80,7 @@ def load() -> C.CDLL:
     lib.sf_profile.argtypes = [i]
     lib.sf_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_longlong), i]
+    lib.sf_profile_collect_phases.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]
     lib.sf_create.argtypes = [C.POINTER(SfConfig), i, C.POINTER(vp)]
     lib.sf_destroy.argtypes = [vp]
     lib.sf_bind_weights.argtypes = [vp, vp, C.POINTER(SfWeightDesc), i]
@@ -131,8 +132,20 @@ PROFILE_CLASSES = ["gemm", "layernorm", "im2col", "temporal_attention", "spatial
                    "kv_append", "other"]
 
 
-def profile(enable: bool) -> None:
-    load().sf_profile(1 if enable else 0)
+def profile(enable) -> None:
+    """False/0 off, True/1 per-kernel events, 2 per-phase events (kernels back to back)."""
+    load().sf_profile(int(enable))
+
+
+PROFILE_PHASES = ["embed", "attention_block", "mlp", "head"]
+
+
+def profile_collect_phases() -> dict:
+    n = len(PROFILE_PHASES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(load().sf_profile_collect_phases(ms, cnt, n), "sf_profile_collect_phases")
+    return {PROFILE_PHASES[k]: {"ms": ms[k], "count": int(cnt[k])} for k in range(n)}
 
 
 def profile_collect() -> dict:

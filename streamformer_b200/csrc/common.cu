@@ -36,8 +36,35 @@ cudaEvent_t take_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 }  // namespace
-void prof_enable(bool on) { g_prof_on = on; }
+// mode 0 off, 1 per-kernel events, 2 per-phase events only (kernels run back to back, PDL intact)
+namespace {
+int g_prof_mode = 0;
+struct PhaseRec { cudaEvent_t a, b; int phase; };
+std::vector<PhaseRec> g_phase_recs;
+}  // namespace
+void prof_set_mode(int mode) { g_prof_mode = mode; g_prof_on = (mode == 1); }
+void prof_enable(bool on) { prof_set_mode(on ? 1 : 0); }
 bool prof_enabled() { return g_prof_on; }
+bool phase_prof_enabled() { return g_prof_mode == 2; }
+void phase_begin(cudaStream_t st, int phase) {
+  PhaseRec r; r.a = take_event(); r.b = take_event(); r.phase = phase;
+  cudaEventRecord(r.a, st);
+  g_phase_recs.push_back(r);
+}
+void phase_end(cudaStream_t st) { if (!g_phase_recs.empty()) cudaEventRecord(g_phase_recs.back().b, st); }
+int phase_collect(double* ms, long long* count, int n) {
+  for (int i = 0; i < n; ++i) { ms[i] = 0; count[i] = 0; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { set_error("phase_collect: %s", cudaGetErrorString(e)); return -2; }
+  for (auto& r : g_phase_recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (r.phase >= 0 && r.phase < n) { ms[r.phase] += t; count[r.phase] += 1; }
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
+  }
+  g_phase_recs.clear();
+  return 0;
+}
 void prof_begin(cudaStream_t st, int cls, double flops, double bytes) {
   ProfRec r; r.a = take_event(); r.b = take_event(); r.cls = cls; r.flops = flops; r.bytes = bytes;
   cudaEventRecord(r.a, st);

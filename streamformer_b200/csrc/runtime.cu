@@ -227,6 +227,8 @@ int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, 
   const int parts_d = gemm_stats_parts(static_cast<int>(M), D);
 
   // ---- temporal branch (…siglip.py:937-958): rows (b,n,t), T innermost => sites are contiguous
+  {
+  PhaseScope phase(st, kPhaseAttnBlock);   // the space-time attention block incl. its projections
   SF_CHECK(gemm(st, dt, x_in, D, lw.t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
                 epi_ln(lw.t_qkv_b, lw.t_qkv_cs, st_in, parts_in, eps)));
   if (kv) {
@@ -260,7 +262,9 @@ int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, 
     e.stats_out = w.stats[1];
     SF_CHECK(gemm(st, dt, w.ctx, D, lw.s_out_w, D, x_out, D, M, D, D, e));
   }
+  }
   // ---- MLP (…siglip.py:997-1000)
+  PhaseScope phase(st, kPhaseMlp);
   {
     GemmEpilogue e = epi_ln(lw.fc1_b, lw.fc1_cs, w.stats[1], parts_d, eps);
     e.act = c->cfg.hidden_act;
@@ -377,7 +381,10 @@ int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int 
   if (b.overflow) { set_error("workspace too small"); return SF_ERR_WORKSPACE; }
   // the im2col operand aliases the (not yet used) MLP buffer: Kp <= I is checked at create time
   void* cur = hidden_states ? hidden_states[0] : x;
-  SF_CHECK(run_embed(c, st, pixels, pix_dtype, B, T, Hh, Ww, time_off, time_total, cur, w.mlp, w.stats[2]));
+  {
+    PhaseScope phase(st, kPhaseEmbed);
+    SF_CHECK(run_embed(c, st, pixels, pix_dtype, B, T, Hh, Ww, time_off, time_total, cur, w.mlp, w.stats[2]));
+  }
   const int parts_d = gemm_stats_parts(static_cast<int>(M), D);
   for (int l = 0; l < c->L; ++l) {
     void* nxt = hidden_states ? hidden_states[l + 1] : cur;
@@ -387,6 +394,7 @@ int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int 
   }
   if (kv) kv->seen += T;
   // post_layernorm, written straight in (b,t,n) order == last_hidden_state (…siglip.py:1330-1346)
+  PhaseScope phase(st, kPhaseHead);
   SF_CHECK(layernorm(st, c->cfg.dtype, cur, D, c->post_g, c->post_b, c->cfg.layer_norm_eps, last_hidden, D, M,
                      D, T > 1 ? kRowBNTtoBTN : kRowIdentity, T, S));
   if (pooler) {
@@ -519,7 +527,8 @@ extern "C" {
 const char* sf_last_error(void) { return last_error(); }
 const char* sf_version(void) { return "streamformer_b200 0.1 (sm_100a)"; }
 uint64_t sf_launch_count(void) { return launch_count(); }
-int sf_profile(int enable) { prof_enable(enable != 0); return 0; }
+int sf_profile(int mode) { prof_set_mode(mode); return 0; }
+int sf_profile_collect_phases(double* ms, long long* count, int n_phases) { return phase_collect(ms, count, n_phases); }
 int sf_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int n_classes) {
   return prof_collect(ms, flops, bytes, launches, n_classes);
 }

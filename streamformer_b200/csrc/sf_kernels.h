@@ -120,7 +120,20 @@ void count_launch(int n = 1);
 enum ProfClass : int { kProfGemm = 0, kProfLayerNorm, kProfIm2col, kProfTemporalAttn, kProfSpatialAttn,
                        kProfPoolAttn, kProfKvAppend, kProfOther, kProfNumClasses };
 void prof_enable(bool on);
+void prof_set_mode(int mode);   // 0 off, 1 per-kernel events, 2 per-phase events only
 bool prof_enabled();
+// Phase timing (mode 2): one event pair around each phase of the forward, kernels inside run
+// back to back exactly as in production (no per-kernel events, PDL overlap intact).
+enum Phase : int { kPhaseEmbed = 0, kPhaseAttnBlock, kPhaseMlp, kPhaseHead, kPhaseNum };
+bool phase_prof_enabled();
+void phase_begin(cudaStream_t st, int phase);
+void phase_end(cudaStream_t st);
+int phase_collect(double* ms, long long* count, int n);
+struct PhaseScope {
+  cudaStream_t st; bool on;
+  PhaseScope(cudaStream_t s, int phase) : st(s), on(phase_prof_enabled()) { if (on) phase_begin(st, phase); }
+  ~PhaseScope() { if (on) phase_end(st); }
+};
 void prof_begin(cudaStream_t st, int cls, double flops, double bytes);
 void prof_end(cudaStream_t st);
 int prof_collect(double* ms, double* flops, double* bytes, long long* launches, int n);
