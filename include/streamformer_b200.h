@@ -127,8 +127,15 @@ int sf_kv_reset(sf_kv* kv);
 int sf_kv_destroy(sf_kv* kv);
 int sf_kv_seq_len(const sf_kv* kv);
 int sf_kv_capacity(const sf_kv* kv);
+/* steps of this cache that were served by replaying a captured CUDA graph (see sf_forward_stream) */
+long long sf_kv_graph_launches(const sf_kv* kv);
 /* forward of T_new frames that attend to every cached frame (+ causal order among the new ones);
- * outputs as sf_forward with T = T_new. Advances the cache by T_new. */
+ * outputs as sf_forward with T = T_new. Advances the cache by T_new.
+ * From the second call with the same (B, T_new, H, W, dtype, workspace) on, the step is replayed
+ * from a CUDA graph captured once: its kernels read the stream position from a device counter the
+ * graph itself advances, so every step of every stream reuses one executable graph and the host
+ * cost per step is two D2D staging copies + one graph launch (SF_STREAM_GRAPH=0 disables;
+ * hidden_states != NULL and the profiling modes use direct launches). */
 int sf_forward_stream(sf_ctx* ctx, void* stream, sf_kv* kv, const void* pixels, int pixels_dtype,
                       int B, int T_new, int H, int W, void* last_hidden, void* pooler,
                       void* const* hidden_states, void* workspace, size_t workspace_bytes);

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "sf_last_error", "sf_version", "sf_launch_count", "sf_profile", "sf_profile_collect", "sf_profile_collect_phases",
     "sf_create", "sf_destroy", "sf_bind_weights", "sf_set_pos_embed",
     "sf_workspace_bytes", "sf_forward",
-    "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_forward_stream",
+    "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_kv_graph_launches", "sf_forward_stream",
     "sf_embed_forward", "sf_layer_forward", "sf_final_norm", "sf_head_forward",
     "sf_op_gemm", "sf_op_layernorm", "sf_op_im2col", "sf_op_temporal_attention", "sf_op_kv_append",
     "sf_op_spatial_attention", "sf_op_pool_attention", "sf_op_rowstats", "sf_op_gemm_stats_parts",
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     lib.sf_kv_destroy.argtypes = [vp]
     lib.sf_kv_seq_len.argtypes = [vp]
     lib.sf_kv_capacity.argtypes = [vp]
+    lib.sf_kv_graph_launches.argtypes = [vp]
     lib.sf_forward_stream.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, vp, C.POINTER(vp), vp, C.c_size_t]
     lib.sf_embed_forward.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp, vp, C.c_size_t]
     lib.sf_layer_forward.argtypes = [vp, vp, i, vp, vp, i, i, i, vp, vp, vp, C.c_size_t]
@@ -108,8 +109,9 @@ def load() -> C.CDLL:
     lib.sf_op_pool_attention.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("sf_last_error", "sf_version", "sf_launch_count"):
+        if name not in ("sf_last_error", "sf_version", "sf_launch_count", "sf_kv_graph_launches"):
             fn.restype = C.c_int
+    lib.sf_kv_graph_launches.restype = C.c_longlong
     _lib = lib
     return lib
 

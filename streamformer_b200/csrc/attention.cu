@@ -130,16 +130,22 @@ struct TemporalArgs {
   int sites, heads, Tq, Tk, q_off, causal, qtiles;
   long tasks;
   float scale_log2;
+  const int* seen_dev;   // streaming under a CUDA graph: q_off = *seen_dev, Tk = q_off + Tq
 };
 
 constexpr int kTWarps = 4;
 
 template <typename T>
-__global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const TemporalArgs a) {
+__global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const TemporalArgs a_in) {
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   __shared__ __align__(128) uint8_t smem[kTWarps][2][16 * 128];  // per warp: K tile, V tile
   griddep_wait();
   griddep_launch_dependents();
+  TemporalArgs a = a_in;
+  if (a.seen_dev) {
+    a.q_off = *a.seen_dev;
+    a.Tk = a.q_off + a.Tq;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, c = lane & 3;
   const long task = static_cast<long>(blockIdx.x) * kTWarps + warp;
@@ -216,9 +222,10 @@ __global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const Tempo
 template <typename T>
 __global__ void __launch_bounds__(256)
 kv_append_kernel(const T* __restrict__ qkv, long ld, T* __restrict__ kc, T* __restrict__ vc, int Tcap,
-                 int sites, int heads, int Tq, int pos0) {
+                 int sites, int heads, int Tq, int pos0, const int* __restrict__ seen_dev) {
   griddep_wait();
   griddep_launch_dependents();
+  if (seen_dev) pos0 = *seen_dev;
   const int D = heads * kHd;
   const long total = static_cast<long>(sites) * Tq * heads * 8;  // 16-byte chunks per K (and per V)
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -463,8 +470,9 @@ int check_launch(const char* what) {
 
 int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, const void* kcache,
                        const void* vcache, int Tcap, void* out, int ld_out, int sites, int heads, int Tq,
-                       int Tk, int q_off, int causal, float scale) {
+                       int Tk, int q_off, int causal, float scale, const int* seen_dev) {
   if (sites <= 0 || Tq <= 0) return 0;
+  if (seen_dev && !kcache) { set_error("temporal_attention: seen_dev needs a cache"); return -1; }
   if (dtype != kBF16 && dtype != kF16) { set_error("temporal_attention: dtype must be bf16/f16"); return -1; }
   if ((ld_qkv % 8) || (ld_out % 2)) { set_error("temporal_attention: bad leading dims"); return -1; }
   const int D = heads * kHd;
@@ -490,6 +498,7 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
   a.qtiles = (Tq + 15) / 16;
   a.tasks = static_cast<long>(sites) * heads * a.qtiles;
   a.scale_log2 = scale * kLog2e;
+  a.seen_dev = seen_dev;
   const long blocks = (a.tasks + kTWarps - 1) / kTWarps;
   ProfScope ps(stream, kProfTemporalAttn, 4.0 * sites * heads * static_cast<double>(Tq) * Tk * kHd,
                2.0 * sites * heads * kHd * (2.0 * Tq + 2.0 * Tk));
@@ -500,7 +509,7 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
 }
 
 int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
-              int Tcap, int sites, int heads, int Tq, int pos0) {
+              int Tcap, int sites, int heads, int Tq, int pos0, const int* seen_dev) {
   if (sites <= 0 || Tq <= 0) return 0;
   if (pos0 + Tq > Tcap) { set_error("kv_append: %d + %d frames exceed cache capacity %d", pos0, Tq, Tcap); return -1; }
   const long total = static_cast<long>(sites) * Tq * heads * 8;
@@ -511,7 +520,7 @@ int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void*
   LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream);
   cudaLaunchKernelEx(&lc.cfg, kv_append_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(qkv),
                      static_cast<long>(ld_qkv), reinterpret_cast<__nv_bfloat16*>(kcache),
-                     reinterpret_cast<__nv_bfloat16*>(vcache), Tcap, sites, heads, Tq, pos0);
+                     reinterpret_cast<__nv_bfloat16*>(vcache), Tcap, sites, heads, Tq, pos0, seen_dev);
   (void)dtype;
   return check_launch("kv_append");
 }

@@ -38,13 +38,41 @@ struct GemmParams {
   int M, N, K;
   void* out;
   int ldo;
+  // tile walk: a work item = one M tile x `group` consecutive N tiles, processed back to back by the
+  // same worker; on the slot path the first `res_kb` K blocks of the item's A tile stay resident
+  // in shared memory for the whole item (fetched once instead of once per N tile)
+  int group;
+  int res_kb;
   GemmEpilogue epi;
+};
+
+// Walks the output tiles of one worker: items are dealt round-robin, the N tiles of an item in order.
+struct TileWalk {
+  int n_tiles, group, groups, num_items, step, item, j;
+  __device__ TileWalk(int M, int N, int tile_m, int bn, int group_, int worker, int workers) {
+    const int m_tiles = (M + tile_m - 1) / tile_m;
+    n_tiles = (N + bn - 1) / bn;
+    group = group_ < 1 ? 1 : group_;
+    groups = (n_tiles + group - 1) / group;
+    num_items = m_tiles * groups;
+    step = workers;
+    item = worker;
+    j = 0;
+  }
+  __device__ bool valid() const { return item < num_items; }
+  __device__ int m_tile() const { return item / groups; }
+  __device__ int n_tile() const { return (item % groups) * group + j; }
+  __device__ bool first_in_item() const { return j == 0; }
+  __device__ bool last_in_item() const { return j + 1 == group || n_tile() + 1 >= n_tiles; }
+  __device__ void next() {
+    if (last_in_item()) { item += step; j = 0; } else { ++j; }
+  }
 };
 
 // CG = CTAs cooperating on one tile (tcgen05 cta_group): 1 -> 128 x BN tile per CTA;
 // 2 -> 256 x BN tile per CTA pair, each CTA staging its 128 A rows and BN/2 of the B rows.
 // EW = epilogue warps (8 or 16).
-template <int BN, int CG, int EW>
+template <int BN, int CG, int EW, bool TS = false>
 struct SmemLayout {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
@@ -58,11 +86,30 @@ struct SmemLayout {
   static constexpr int kAuxBytes = 2 * kAuxBytesPerStage;
   static constexpr int kBudget = 232448 - 1024 - 256 - kAuxBytes;   // 227 KB minus alignment slack, barriers, aux
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
-  static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kAuxOffset = kBarOffset + 256;
-  static constexpr int kTotal = kAuxOffset + kAuxBytes + 1024;
+  // Slot path (CTA pairs, 256 x 256 tiles): the A part and the B part of a K block are both 16 KB,
+  // so operand memory is kSlots uniform 16 KB slots.  The first res_kb slots hold resident A K
+  // blocks of the current work item, the rest form the ring every other operand block streams through.
+  static constexpr bool kSlotPath = (CG == 2 && BN == 256);
+  static constexpr int kSlotBytes = 16384;
+  // TS (TMA-store epilogue): every epilogue warp owns three staging buffers of 32 rows x one chunk
+  // (32 or 16 columns) through which its output — and its residual, when there is one — moves
+  // between registers and global memory as whole TMA boxes.
+  static constexpr int kChunkCols = (EW == 16) ? 16 : 32;
+  static constexpr int kStageBufBytes = 32 * kChunkCols * 2;
+  static constexpr int kStagingBytes = TS ? EW * 3 * kStageBufBytes : 0;
+  static constexpr int kSlots = TS ? 10 : 13;
+  static constexpr int kMaxRes = kSlots - 4;        // leaves a ring of >= 4 slots
+  static constexpr int kBarBytes = kSlotPath ? 1024 : 256;
+  static constexpr int kBarOffset = kSlotPath ? kSlots * kSlotBytes : kStages * kStageBytes;
+  static constexpr int kAuxOffset = kBarOffset + kBarBytes;
+  static constexpr int kStagingOffset = kAuxOffset + kAuxBytes;
+  static constexpr int kTotal = kStagingOffset + kStagingBytes + 1024;
+  static_assert(!TS || kSlotPath, "the TMA-store epilogue exists on the slot path only");
   static_assert(kStages >= 3, "not enough shared memory for a 3-stage pipeline");
   static_assert(2 * kStages + 8 <= 31, "barrier area overflow");
+  static_assert(!kSlotPath || (kABytes == kSlotBytes && kBBytes == kSlotBytes), "slot path needs 16 KB operand blocks");
+  static_assert(!kSlotPath || (2 * kSlots + 2 * kMaxRes + 8 + 1 + 3 * EW) * 8 <= kBarBytes, "slot barrier area overflow");
+  static_assert(kTotal <= 232448, "shared memory budget exceeded");
 };
 
 template <typename T> struct UmmaFmt;
@@ -128,6 +175,12 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
 __device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void lds128u(uint32_t addr, uint32_t* v) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, const uint32_t* v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
 // 16 consecutive 2-byte elements of one row <-> 8 registers.  `wide`: the row is 32-byte aligned, so
 // one 256-bit access (a full 32-byte sector per lane; sm_100 LDG/STG.256) moves them; otherwise two
 // 128-bit accesses.  ncols = valid columns at p (a multiple of 8; < 16 only on a ragged N edge).
@@ -160,11 +213,12 @@ __device__ __forceinline__ void stg_cols16(void* p, const uint32_t (&v)[8], int 
   }
 }
 
-template <typename T, int BN, int CG, int EPI, int EW>
+template <typename T, int BN, int CG, int EPI, int EW, bool TS>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                     const GemmParams p) {
-  using L = SmemLayout<BN, CG, EW>;
+  using L = SmemLayout<BN, CG, EW, TS>;
   constexpr int kStages = L::kStages;
   constexpr int kTileM = kBM * CG;
   constexpr bool kLnCapable = (EPI == kEpiBias || EPI == kEpiAct);
@@ -173,13 +227,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // SWIZZLE_128B operand tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  constexpr bool kSlotPath = L::kSlotPath;
+  constexpr int kRingBars = kSlotPath ? L::kSlots : kStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);   // stage ring / slot ring
+  uint64_t* empty_bar = full_bar + kRingBars;
+  uint64_t* res_full = empty_bar + kRingBars;                               // slot path: resident A blocks
+  uint64_t* res_empty = res_full + (kSlotPath ? L::kMaxRes : 0);
+  uint64_t* tmem_full = res_empty + (kSlotPath ? L::kMaxRes : 0);
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* aux_full = tmem_empty + 2;
   uint64_t* aux_empty = aux_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + 2);
+  uint64_t* res_bar = aux_empty + 3;     // TS + residual: three per epilogue warp (one per staging buffer)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -188,17 +247,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int worker = blockIdx.x / CG;          // one worker = one CTA (CG=1) or one CTA pair (CG=2)
   const int num_workers = gridDim.x / CG;
 
-  const int m_tiles = (p.M + kTileM - 1) / kTileM;
-  const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + kBK - 1) / kBK;
+  const int group = kSlotPath ? p.group : 1;
+  // resident A K blocks (slot path only); the ring keeps the remaining slots
+  const int res_kb = kSlotPath ? (p.res_kb < k_blocks ? p.res_kb : k_blocks) : 0;
+  const int ring = L::kSlots - res_kb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kRingBars; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    if constexpr (kSlotPath) {
+      for (int s = 0; s < L::kMaxRes; ++s) {
+        mbar_init(&res_full[s], 1);
+        mbar_init(&res_empty[s], 1);
+      }
+    }
+    if constexpr (TS) {
+      tma_prefetch_desc(&tmOut);
+      if constexpr (EPI == kEpiResidual) {
+        tma_prefetch_desc(&tmRes);
+        for (int i = 0; i < 3 * EW; ++i) mbar_init(&res_bar[i], 1);
+      }
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -230,12 +303,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (every CTA)
-    if (elect_one_sync()) {
+    if constexpr (kSlotPath) {
+      if (elect_one_sync()) {
+        int slot = 0;              // ring position (slots res_kb .. kSlots-1)
+        uint32_t phase = 0;
+        int items_done = 0;
+        uint8_t* ring_base = smem + res_kb * L::kSlotBytes;
+        auto ring_load = [&](const CUtensorMap* tm, int c0, int c1) {
+          mbar_wait(&empty_bar[slot], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[slot], 2 * L::kSlotBytes);
+          tma_load_2d_cg2(ring_base + slot * L::kSlotBytes, tm, &full_bar[slot], c0, c1);
+          if (++slot == ring) { slot = 0; phase ^= 1; }
+        };
+        for (TileWalk w(p.M, p.N, kTileM, BN, group, worker, num_workers); w.valid(); w.next()) {
+          const int m0 = w.m_tile() * kTileM + static_cast<int>(cta_rank) * kBM;
+          const int n0 = w.n_tile() * BN + static_cast<int>(cta_rank) * (BN / CG);
+          const bool first = w.first_in_item();
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            if (kb < res_kb) {
+              if (first) {   // A block fetched once per item, into its resident slot
+                mbar_wait(&res_empty[kb], (items_done & 1) ^ 1);
+                if (leader) mbar_arrive_expect_tx(&res_full[kb], 2 * L::kSlotBytes);
+                tma_load_2d_cg2(smem + kb * L::kSlotBytes, &tmA, &res_full[kb], kb * kBK, m0);
+              }
+            } else {
+              ring_load(&tmA, kb * kBK, m0);
+            }
+            ring_load(&tmB, kb * kBK, n0);
+          }
+          if (w.last_in_item()) ++items_done;
+        }
+      }
+    } else if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        const int m0 = (tile / n_tiles) * kTileM + static_cast<int>(cta_rank) * kBM;
-        const int n0 = (tile % n_tiles) * BN + static_cast<int>(cta_rank) * (BN / CG);
+      for (TileWalk w(p.M, p.N, kTileM, BN, 1, worker, num_workers); w.valid(); w.next()) {
+        const int m0 = w.m_tile() * kTileM + static_cast<int>(cta_rank) * kBM;
+        const int n0 = w.n_tile() * BN + static_cast<int>(cta_rank) * (BN / CG);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -260,12 +364,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && elect_one_sync()) {
-      constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, UmmaFmt<T>::value);
+    constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, UmmaFmt<T>::value);
+    if constexpr (kSlotPath) {
+      if (leader && elect_one_sync()) {
+        int slot = 0;
+        uint32_t phase = 0;
+        int items_done = 0, it = 0;
+        const uint32_t ring_u = smem_u32(smem + res_kb * L::kSlotBytes);
+        for (TileWalk w(p.M, p.N, kTileM, BN, group, worker, num_workers); w.valid(); w.next(), ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          const bool first = w.first_in_item(), last = w.last_in_item();
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            uint32_t sa;
+            int a_slot = -1;
+            if (kb < res_kb) {
+              if (first) mbar_wait(&res_full[kb], items_done & 1);
+              sa = smem_u32(smem + kb * L::kSlotBytes);
+            } else {
+              mbar_wait(&full_bar[slot], phase);
+              a_slot = slot;
+              sa = ring_u + slot * L::kSlotBytes;
+              if (++slot == ring) { slot = 0; phase ^= 1; }
+            }
+            mbar_wait(&full_bar[slot], phase);
+            const int b_slot = slot;
+            const uint32_t sb = ring_u + slot * L::kSlotBytes;
+            if (++slot == ring) { slot = 0; phase ^= 1; }
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128_kmajor(sa);
+            const uint64_t db = umma_desc_sw128_kmajor(sb);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            // hand the operand slots back (in both CTAs of the pair) when these MMAs retire
+            if (a_slot >= 0) umma_commit_cg2_mc(&empty_bar[a_slot], 0x3);
+            umma_commit_cg2_mc(&empty_bar[b_slot], 0x3);
+            if (kb < res_kb && last) umma_commit_cg2_mc(&res_empty[kb], 0x3);
+          }
+          umma_commit_cg2_mc(&tmem_full[acc], 0x3);
+          if (last) ++items_done;
+        }
+      }
+    } else if (leader && elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+      for (TileWalk w(p.M, p.N, kTileM, BN, 1, worker, num_workers); w.valid(); w.next(), ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -304,12 +452,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // LayerNorm (-mean, rstd) of the tile's 128 rows, reduced from the producer's partials.
     const float inv_k = 1.0f / static_cast<float>(p.K);
     int it = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+    for (TileWalk w(p.M, p.N, kTileM, BN, group, worker, num_workers); w.valid(); w.next(), ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * kTileM + static_cast<int>(cta_rank) * kBM;
-      const int n0 = (tile % n_tiles) * BN;
-      if constexpr (EPI == kEpiResidual) {
+      const int m0 = w.m_tile() * kTileM + static_cast<int>(cta_rank) * kBM;
+      const int n0 = w.n_tile() * BN;
+      if constexpr (EPI == kEpiResidual && !TS) {
         // pull the tile's residual rows into L2 a whole tile ahead of the epilogue's loads
         const int left = p.N - n0;
         const uint32_t bytes = static_cast<uint32_t>((left < BN ? left : BN) * 2) & ~15u;
@@ -321,55 +469,272 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             prefetch_l2_bulk(resb + map_out_row(m, e.row_map, e.T, e.S) * e.ldr + n0, bytes);
         }
       }
-      mbar_wait(&aux_empty[st], ph ^ 1);
-      const uint32_t aux_u = smem_u32(smem + L::kAuxOffset + st * L::kAuxBytesPerStage);
+      // Issue every global load of the tile first (bias / column-sum slices and all row-statistics
+      // partials of the 128 rows), then wait for the stage: one memory round trip per tile instead
+      // of one per row group — this warp must never be slower than the epilogue it feeds.
+      constexpr int kVec = BN / 4 / 32;                 // float4 per lane per table (2 for BN=256, 1 for 128)
+      float4 b4[kVec], c4[kVec];
 #pragma unroll
-      for (int i = lane; i < BN / 4; i += 32) {
-        const int col = n0 + i * 4;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = b4;
+      for (int v = 0; v < kVec; ++v) {
+        const int col = n0 + (v * 32 + lane) * 4;
+        b4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        c4[v] = b4[v];
         if (col < p.N) {
-          if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-          if (ln) c4 = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + col));
+          if (e.bias) b4[v] = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+          if (ln) c4[v] = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + col));
         }
-        sts128f(aux_u + L::kAuxBias + i * 16, b4);
-        if constexpr (kLnCapable) sts128f(aux_u + L::kAuxColsum + i * 16, c4);
       }
+      constexpr int kMaxParts = 6;                      // partials held in registers per row
+      float2 t[kBM / 32][kMaxParts];
+      float s1x[kBM / 32], s2x[kBM / 32];
       if constexpr (kLnCapable) {
         if (ln) {
-          constexpr int kMaxParts = 12;
 #pragma unroll
           for (int rr = 0; rr < kBM / 32; ++rr) {
-            const int row = rr * 32 + lane;
-            const int m = m0 + row;
-            float2 t[kMaxParts];
+            const int m = m0 + rr * 32 + lane;
 #pragma unroll
             for (int q = 0; q < kMaxParts; ++q) {
-              t[q] = make_float2(0.f, 0.f);
-              if (q < e.ln_parts && m < p.M) t[q] = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
+              t[rr][q] = make_float2(0.f, 0.f);
+              if (q < e.ln_parts && m < p.M) t[rr][q] = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
             }
+          }
+#pragma unroll
+          for (int rr = 0; rr < kBM / 32; ++rr) {
+            const int m = m0 + rr * 32 + lane;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int q = 0; q < kMaxParts; ++q) {
-              s1 += t[q].x;
-              s2 += t[q].y;
+              s1 += t[rr][q].x;
+              s2 += t[rr][q].y;
             }
-            for (int q = kMaxParts; q < e.ln_parts; ++q) {   // (never with the shipped tile shapes)
+            for (int q = kMaxParts; q < e.ln_parts; ++q) {   // more partials than registers (small-N producers)
               if (m < p.M) {
                 const float2 u = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
                 s1 += u.x;
                 s2 += u.y;
               }
             }
-            const float mean = s1 * inv_k;
-            const float var = fmaxf(fmaf(s2, inv_k, -mean * mean), 0.f);
+            s1x[rr] = s1;
+            s2x[rr] = s2;
+          }
+        }
+      }
+      mbar_wait(&aux_empty[st], ph ^ 1);
+      const uint32_t aux_u = smem_u32(smem + L::kAuxOffset + st * L::kAuxBytesPerStage);
+#pragma unroll
+      for (int v = 0; v < kVec; ++v) {
+        sts128f(aux_u + L::kAuxBias + (v * 32 + lane) * 16, b4[v]);
+        if constexpr (kLnCapable) sts128f(aux_u + L::kAuxColsum + (v * 32 + lane) * 16, c4[v]);
+      }
+      if constexpr (kLnCapable) {
+        if (ln) {
+#pragma unroll
+          for (int rr = 0; rr < kBM / 32; ++rr) {
+            const float mean = s1x[rr] * inv_k;
+            const float var = fmaxf(fmaf(s2x[rr], inv_k, -mean * mean), 0.f);
             const float rstd = rsqrtf(var + e.ln_eps);
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(aux_u + L::kAuxRows + row * 8), "f"(-mean), "f"(rstd)
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(aux_u + L::kAuxRows + (rr * 32 + lane) * 8), "f"(-mean), "f"(rstd)
                          : "memory");
           }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&aux_full[st]);
+    }
+  } else if (warp >= 4 && TS) {
+    // ------------------------------------------------------------------ epilogue warps, TMA-store path
+    // Thread == accumulator row (TMEM lane), 32- (or 16-) column chunks as below, but nothing touches
+    // global memory with per-thread accesses (a row-per-lane 32-byte store costs the LSU data pipe
+    // ~45 wavefronts per KB and made the epilogue, not the tensor pipe, the bound of every K=768
+    // GEMM): a chunk is written to a swizzled staging buffer (conflict-free STS.128) and leaves as
+    // ONE TMA box store per warp; the residual arrives the same way, requested two chunks ahead
+    // into the buffer the output will later leave from.  Three buffers per warp rotate.
+    if constexpr (TS) {
+    const int ew = warp - 4;
+    const int quarter = warp & 3;
+    const int colgrp = ew >> 2;
+    constexpr int kColsPerWarp = BN / (EW / 4);
+    constexpr int kCW = L::kChunkCols;
+    constexpr int kChunks = kColsPerWarp / kCW;
+    constexpr int kRowBytes = kCW * 2;
+    constexpr int kBufBytes = L::kStageBufBytes;
+    constexpr int kC16 = kRowBytes / 16;            // 16-byte pieces per staged row
+    static_assert(kChunks % 2 == 0, "chunks are processed in double-buffered pairs");
+    const bool want_stats = kStatsCapable && e.stats_out != nullptr;
+    const float gscale = e.gate ? tanhf(__ldg(e.gate)) : 1.0f;
+    uint8_t* stg = smem + L::kStagingOffset + ew * (3 * kBufBytes);
+    const uint32_t stg_u = smem_u32(stg);
+    uint64_t* rbar = res_bar + ew * 3;
+    // CU_TENSOR_MAP_SWIZZLE_64B / _32B: 16-byte piece index ^= (row / (128 / row bytes)) mod pieces
+    const uint32_t swz = (static_cast<uint32_t>(lane) / (128 / kRowBytes)) & (kC16 - 1);
+    const uint32_t my_row_u = static_cast<uint32_t>(lane) * kRowBytes;
+    uint32_t f = 0;        // chunks processed by this warp so far: buffer f % 3, barrier parity (f / 3) & 1
+    // residual look-ahead: (tile, chunk) of the next residual box to request (lane 0 only)
+    TileWalk wl(p.M, p.N, kTileM, BN, group, worker, num_workers);
+    int lc = 0;
+    uint32_t lf = 0;
+    auto issue_res = [&]() {
+      if (!wl.valid()) return;
+      const int lrow = wl.m_tile() * kTileM + static_cast<int>(cta_rank) * kBM + quarter * 32;
+      const int lcol = wl.n_tile() * BN + colgrp * kColsPerWarp + lc * kCW;
+      const uint32_t b = lf % 3;
+      mbar_arrive_expect_tx(&rbar[b], kBufBytes);
+      tma_load_2d(stg + b * kBufBytes, &tmRes, &rbar[b], lcol, lrow);
+      ++lf;
+      if (++lc == kChunks) { lc = 0; wl.next(); }
+    };
+    if constexpr (EPI == kEpiResidual) {
+      if (lane == 0) { issue_res(); issue_res(); }
+    }
+    int it = 0;
+    for (TileWalk w(p.M, p.N, kTileM, BN, group, worker, num_workers); w.valid(); w.next(), ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = w.m_tile() * kTileM + static_cast<int>(cta_rank) * kBM;
+      const int n0 = w.n_tile() * BN;
+      const int row0 = m0 + quarter * 32;
+      const int m = row0 + lane;
+      const bool row_ok = m < p.M;
+      const int wcol0 = n0 + colgrp * kColsPerWarp;
+      const uint32_t aux_u = smem_u32(smem + L::kAuxOffset + acc * L::kAuxBytesPerStage);
+      const uint32_t bias_u = aux_u + L::kAuxBias + colgrp * kColsPerWarp * 4;
+      const uint32_t csum_u = aux_u + L::kAuxColsum + colgrp * kColsPerWarp * 4;
+      mbar_wait(&aux_full[acc], acc_phase);
+      float nmean = 0.f, rstd = 1.f;
+      if constexpr (kLnCapable) {
+        if (ln) {
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(nmean), "=f"(rstd)
+                       : "r"(aux_u + L::kAuxRows + (quarter * 32 + lane) * 8));
+        }
+      }
+      float st1 = 0.f, st2 = 0.f;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
+                              colgrp * kColsPerWarp;
+      uint32_t raw[2][kCW];
+      auto tmem_fetch = [&](int c, uint32_t (&dst)[kCW]) {
+        if constexpr (kCW == 32) tmem_ld_32x32b_x32(t_base + c * kCW, dst);
+        else tmem_ld_32x32b_x16(t_base + c * kCW, dst);
+      };
+      tmem_fetch(0, raw[0]);
+#pragma unroll 1
+      for (int cp = 0; cp < kChunks / 2; ++cp) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = cp * 2 + h;
+          const int col0 = wcol0 + c * kCW;
+          tmem_ld_wait();                                     // chunk c is in registers
+          if (c + 1 < kChunks) {
+            tmem_fetch(c + 1, raw[h ^ 1]);
+          } else {
+            // last TMEM read of this accumulator is done: hand it back to the MMA warp now, the
+            // rest of the tile's epilogue overlaps the next-but-one tile's main loop
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+            }
+          }
+          const uint32_t buf = f % 3;
+          const uint32_t buf_u = stg_u + buf * kBufBytes;
+          uint32_t rb[kCW / 2];
+          if constexpr (EPI == kEpiResidual) {
+            mbar_wait(&rbar[buf], (f / 3) & 1);
+#pragma unroll
+            for (int q = 0; q < kC16; ++q) lds128u(buf_u + my_row_u + ((static_cast<uint32_t>(q) ^ swz) << 4), &rb[q * 4]);
+          }
+          uint32_t ob[kCW / 2];
+#pragma unroll
+          for (int g = 0; g < kCW / 8; ++g) {  // groups of 8 columns
+            float vv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = __uint_as_float(raw[h][g * 8 + j]);
+            const float4 b0 = lds128f(bias_u + (c * kCW + g * 8) * 4);
+            const float4 b1 = lds128f(bias_u + (c * kCW + g * 8 + 4) * 4);
+            bool did_ln = false;
+            if constexpr (kLnCapable) {
+              if (ln) {
+                const float4 c0 = lds128f(csum_u + (c * kCW + g * 8) * 4);
+                const float4 c1 = lds128f(csum_u + (c * kCW + g * 8 + 4) * 4);
+                vv[0] = fmaf(rstd, fmaf(nmean, c0.x, vv[0]), b0.x); vv[1] = fmaf(rstd, fmaf(nmean, c0.y, vv[1]), b0.y);
+                vv[2] = fmaf(rstd, fmaf(nmean, c0.z, vv[2]), b0.z); vv[3] = fmaf(rstd, fmaf(nmean, c0.w, vv[3]), b0.w);
+                vv[4] = fmaf(rstd, fmaf(nmean, c1.x, vv[4]), b1.x); vv[5] = fmaf(rstd, fmaf(nmean, c1.y, vv[5]), b1.y);
+                vv[6] = fmaf(rstd, fmaf(nmean, c1.z, vv[6]), b1.z); vv[7] = fmaf(rstd, fmaf(nmean, c1.w, vv[7]), b1.w);
+                did_ln = true;
+              }
+            }
+            if (!did_ln) {
+              vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+              vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+            }
+            if constexpr (EPI == kEpiAct) {
+              if (e.act == kActGeluErf) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
+              }
+            }
+            if constexpr (EPI == kEpiResidual) {
+              const uint32_t* rq = &rb[g * 4];
+              const float2 r0 = Pack2<T>::unpack(rq[0]), r1 = Pack2<T>::unpack(rq[1]);
+              const float2 r2 = Pack2<T>::unpack(rq[2]), r3 = Pack2<T>::unpack(rq[3]);
+              vv[0] = fmaf(gscale, vv[0], r0.x); vv[1] = fmaf(gscale, vv[1], r0.y);
+              vv[2] = fmaf(gscale, vv[2], r1.x); vv[3] = fmaf(gscale, vv[3], r1.y);
+              vv[4] = fmaf(gscale, vv[4], r2.x); vv[5] = fmaf(gscale, vv[5], r2.y);
+              vv[6] = fmaf(gscale, vv[6], r3.x); vv[7] = fmaf(gscale, vv[7], r3.y);
+            } else if constexpr (EPI == kEpiBias) {
+              if (e.gate) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] *= gscale;
+              }
+            }
+            uint32_t* oq = &ob[g * 4];
+            oq[0] = Pack2<T>::pack(vv[0], vv[1]); oq[1] = Pack2<T>::pack(vv[2], vv[3]);
+            oq[2] = Pack2<T>::pack(vv[4], vv[5]); oq[3] = Pack2<T>::pack(vv[6], vv[7]);
+            if constexpr (kStatsCapable) {
+              if (want_stats) {   // statistics of the values as stored (rounded), what the next GEMM multiplies
+                const float2 q0 = Pack2<T>::unpack(oq[0]), q1 = Pack2<T>::unpack(oq[1]);
+                const float2 q2 = Pack2<T>::unpack(oq[2]), q3 = Pack2<T>::unpack(oq[3]);
+                st1 += ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+                st2 = fmaf(q0.x, q0.x, fmaf(q0.y, q0.y, fmaf(q1.x, q1.x, fmaf(q1.y, q1.y, st2))));
+                st2 = fmaf(q2.x, q2.x, fmaf(q2.y, q2.y, fmaf(q3.x, q3.x, fmaf(q3.y, q3.y, st2))));
+              }
+            }
+          }
+          // the staging buffer changes hands: residual in -> output out
+          if constexpr (EPI == kEpiResidual) {
+            __syncwarp();                                   // every lane has read its residual row
+          } else {
+            if (lane == 0) tma_store_wait_read<2>();        // the store that last used this buffer has drained it
+            __syncwarp();
+          }
+#pragma unroll
+          for (int q = 0; q < kC16; ++q) sts128u(buf_u + my_row_u + ((static_cast<uint32_t>(q) ^ swz) << 4), &ob[q * 4]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (row0 < p.M) tma_store_2d(&tmOut, stg + buf * kBufBytes, col0, row0);
+            tma_store_commit();
+            if constexpr (EPI == kEpiResidual) {
+              tma_store_wait_read<1>();                     // buffers of chunks <= f-1 are free again
+              issue_res();                                  // residual of chunk f+2 -> buffer (f+2) % 3
+            }
+          }
+          ++f;
+        }
+      }
+      if constexpr (kStatsCapable) {
+        if (want_stats && row_ok)
+          e.stats_out[static_cast<long>(wcol0 / kColsPerWarp) * p.M + m] = make_float2(st1, st2);
+      }
+      // all reads of the aux stage are complete -> hand it back (the accumulator went back above)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aux_empty[acc]);
+    }
+    if (lane == 0) tma_store_wait<0>();   // staged data must stay valid until the last store has read it
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue warps
@@ -394,11 +759,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool wide_out = ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) && (p.ldo % 16 == 0);
     const bool wide_res = ((reinterpret_cast<uintptr_t>(e.residual) & 31) == 0) && (e.ldr % 16 == 0);
     int it = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+    for (TileWalk w(p.M, p.N, kTileM, BN, group, worker, num_workers); w.valid(); w.next(), ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * kTileM + static_cast<int>(cta_rank) * kBM;
-      const int n0 = (tile % n_tiles) * BN;
+      const int m0 = w.m_tile() * kTileM + static_cast<int>(cta_rank) * kBM;
+      const int n0 = w.n_tile() * BN;
       const int m = m0 + quarter * 32 + lane;
       const bool row_ok = m < p.M;
       // row decomposition / permutation
@@ -423,8 +788,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float* time_row = nullptr;
       if constexpr (EPI == kEpiEmbed) {
         if (e.pos) pos_row = e.pos + static_cast<long>(site) * p.N;
-        if (e.time_emb)
-          time_row = e.time_emb + static_cast<long>(time_index(e.time_off + frame, e.time_len, e.time_total)) * p.N;
+        if (e.time_emb) {
+          int t_off = e.time_off, t_total = e.time_total;
+          if (e.time_off_dev) {
+            t_off = __ldg(e.time_off_dev);
+            t_total = t_off + e.T > e.time_horizon ? t_off + e.T : e.time_horizon;
+          }
+          time_row = e.time_emb + static_cast<long>(time_index(t_off + frame, e.time_len, t_total)) * p.N;
+        }
       }
       const int wcol0 = n0 + colgrp * kColsPerWarp;
       T* orow = out + r * p.ldo;
@@ -583,6 +954,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // ------------------------------------------------------------------------------- host side
 // 2D K-major operand map: dims {K, rows}, box {64, box_rows}, 128B swizzle, zero OOB fill.
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 int make_operand_map(CUtensorMap* map, int dtype, const void* base, int rows, int K, int ld,
                      int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -604,16 +980,82 @@ int make_operand_map(CUtensorMap* map, int dtype, const void* base, int rows, in
   return 0;
 }
 
-template <typename T, int BN, int CG, int EPI, int EW>
+// Slot path: how many consecutive N tiles one work item covers (G) and how many A K blocks stay
+// resident for the item (R).  The main loop of a 256 x 256 CTA-pair tile is bound by operand ingest
+// (~46 B per SM clock from L2, profiles/r1_ncu_layer.md) before it is bound by the tensor pipe
+// (512 clk per 64-wide K block), so re-using A across the N tiles of an item shortens every tile
+// after the first; larger groups leave fewer items to balance over the workers.  Pick the G that
+// minimises rounds x (first tile + (G-1) later tiles).
+void pick_group(int m_tiles, int n_tiles, int k_blocks, int workers, int max_res, int* G_out, int* R_out) {
+  // measured on B200: grouping + resident A is neutral (the K=768 GEMMs were epilogue-bound, not
+  // ingest-bound), so it is opt-in: SF_GEMM_GROUP=g forces groups of g N tiles, 0 = cost model
+  static const int forced_g = env_int("SF_GEMM_GROUP", 1);
+  static const int forced_r = env_int("SF_GEMM_RES", -1);
+  int rmax = forced_r >= 0 ? forced_r : 8;
+  if (rmax > max_res) rmax = max_res;
+  if (rmax > k_blocks) rmax = k_blocks;
+  const double mma = 512.0 * k_blocks, rate = 46.0;
+  const double first = 2.0 * k_blocks * 16384.0 / rate;
+  const double later = (2.0 * k_blocks - rmax) * 16384.0 / rate;
+  double best = 1e30;
+  int bg = 1;
+  for (int g = 1; g <= 6 && g <= n_tiles; ++g) {
+    if (forced_g > 0 && g != (forced_g < n_tiles ? forced_g : n_tiles)) continue;
+    if (g > 1 && rmax == 0) break;
+    const long items = static_cast<long>(m_tiles) * ((n_tiles + g - 1) / g);
+    const long rounds = (items + workers - 1) / workers;
+    const double cost = rounds * ((first > mma ? first : mma) + (g - 1) * (later > mma ? later : mma));
+    if (cost < best * 0.999) { best = cost; bg = g; }
+  }
+  *G_out = bg;
+  *R_out = bg > 1 ? rmax : 0;
+}
+
+// 2D map of an output / residual matrix for the TMA-store epilogue: dims {cols, rows}, box
+// {box_cols, 32}, swizzle matching the staged row size (64 or 32 bytes).
+int make_io_map(CUtensorMap* map, int dtype, const void* base, int rows, int cols, int ld, int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -3;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt =
+      dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(io map) failed (%d): rows=%d cols=%d ld=%d base=%p", (int)r, rows, cols, ld, base);
+    return -3;
+  }
+  return 0;
+}
+
+template <typename T, int BN, int CG, int EPI, int EW, bool TS>
 int launch_gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw,
-                const GemmParams& p) {
-  using L = SmemLayout<BN, CG, EW>;
-  CUtensorMap tmA, tmB;
+                const GemmParams& p_in) {
+  using L = SmemLayout<BN, CG, EW, TS>;
+  GemmParams p = p_in;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
   int rc = make_operand_map(&tmA, dtype, A, p.M, p.K, lda, kBM);
   if (rc) return rc;
   rc = make_operand_map(&tmB, dtype, W, p.N, p.K, ldw, BN / CG);
   if (rc) return rc;
-  auto kernel = gemm_tcgen05_kernel<T, BN, CG, EPI, EW>;
+  if constexpr (TS) {
+    rc = make_io_map(&tmOut, dtype, p.out, p.M, p.N, p.ldo, L::kChunkCols);
+    if (rc) return rc;
+    if (p.epi.residual) {
+      rc = make_io_map(&tmRes, dtype, p.epi.residual, p.M, p.N, p.epi.ldr, L::kChunkCols);
+      if (rc) return rc;
+    } else {
+      tmRes = tmOut;
+    }
+  } else {
+    tmOut = tmA;   // unused by the kernel
+    tmRes = tmA;
+  }
+  auto kernel = gemm_tcgen05_kernel<T, BN, CG, EPI, EW, TS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -625,16 +1067,19 @@ int launch_gemm(cudaStream_t stream, int dtype, const void* A, int lda, const vo
   }
   const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles;
   const int max_workers = num_sms() / CG;
-  const int workers = tiles < max_workers ? tiles : max_workers;
+  p.group = 1;
+  p.res_kb = 0;
+  if constexpr (L::kSlotPath) pick_group(m_tiles, n_tiles, (p.K + kBK - 1) / kBK, max_workers, L::kMaxRes, &p.group, &p.res_kb);
+  const int items = m_tiles * ((n_tiles + p.group - 1) / p.group);
+  const int workers = items < max_workers ? items : max_workers;
   LaunchCfg lc(dim3(static_cast<unsigned>(workers * CG)), dim3(128 + EW * 32), L::kTotal, stream, CG);
   cudaError_t e;
   {
     ProfScope ps(stream, kProfGemm, 2.0 * p.M * p.N * p.K,
                  2.0 * (static_cast<double>(p.M) * p.K + static_cast<double>(p.N) * p.K +
                         static_cast<double>(p.M) * p.N * (p.epi.residual ? 2 : 1)));
-    e = cudaLaunchKernelEx(&lc.cfg, kernel, tmA, tmB, p);
+    e = cudaLaunchKernelEx(&lc.cfg, kernel, tmA, tmB, tmOut, tmRes, p);
   }
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
@@ -643,11 +1088,6 @@ int launch_gemm(cudaStream_t stream, int dtype, const void* A, int lda, const vo
     return -2;
   }
   return 0;
-}
-
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
 }
 
 // Tile shape for an M x N output: 0 -> 256 x 256 on CTA pairs (cta_group::2: half the B traffic per
@@ -676,17 +1116,25 @@ template <typename T, int EPI>
 int dispatch_shape(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw,
                    const GemmParams& p) {
   const int shape = pick_shape(p.M, p.N);
+  // TMA-store epilogue: CTA-pair tiles writing rows in GEMM order (SF_GEMM_TS=0: per-thread stores)
+  static const bool ts_on = env_int("SF_GEMM_TS", 1) != 0;
+  if constexpr (EPI != kEpiEmbed) {
+    if (shape == 0 && ts_on && p.epi.row_map == kRowIdentity) {
+      if (pick_epi_warps(EPI, p.epi) == 16) return launch_gemm<T, 256, 2, EPI, 16, true>(stream, dtype, A, lda, W, ldw, p);
+      return launch_gemm<T, 256, 2, EPI, 8, true>(stream, dtype, A, lda, W, ldw, p);
+    }
+  }
   if (pick_epi_warps(EPI, p.epi) == 16) {
     switch (shape) {
-      case 0: return launch_gemm<T, 256, 2, EPI, 16>(stream, dtype, A, lda, W, ldw, p);
-      case 1: return launch_gemm<T, 256, 1, EPI, 16>(stream, dtype, A, lda, W, ldw, p);
-      default: return launch_gemm<T, 128, 1, EPI, 16>(stream, dtype, A, lda, W, ldw, p);
+      case 0: return launch_gemm<T, 256, 2, EPI, 16, false>(stream, dtype, A, lda, W, ldw, p);
+      case 1: return launch_gemm<T, 256, 1, EPI, 16, false>(stream, dtype, A, lda, W, ldw, p);
+      default: return launch_gemm<T, 128, 1, EPI, 16, false>(stream, dtype, A, lda, W, ldw, p);
     }
   }
   switch (shape) {
-    case 0: return launch_gemm<T, 256, 2, EPI, 8>(stream, dtype, A, lda, W, ldw, p);
-    case 1: return launch_gemm<T, 256, 1, EPI, 8>(stream, dtype, A, lda, W, ldw, p);
-    default: return launch_gemm<T, 128, 1, EPI, 8>(stream, dtype, A, lda, W, ldw, p);
+    case 0: return launch_gemm<T, 256, 2, EPI, 8, false>(stream, dtype, A, lda, W, ldw, p);
+    case 1: return launch_gemm<T, 256, 1, EPI, 8, false>(stream, dtype, A, lda, W, ldw, p);
+    default: return launch_gemm<T, 128, 1, EPI, 8, false>(stream, dtype, A, lda, W, ldw, p);
   }
 }
 

@@ -5,6 +5,7 @@
 // KV cache (downstream/VideoQA/llava/model/multimodal_encoder/timesformer_encoder.py:307-375,
 // 491-560, 1340-1349).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -153,9 +154,28 @@ struct sf_ctx {
   float *head_q = nullptr, *head_ln_g = nullptr, *head_ln_b = nullptr;
 };
 
+// One captured streaming step (sf_forward_stream under a CUDA graph): fixed shapes and buffers, the
+// position in the stream is read by the kernels from sf_kv::d_seen.
+struct StreamGraph {
+  cudaGraphExec_t exec = nullptr;
+  int B = 0, T = 0, H = 0, W = 0, pix_dtype = 0;
+  bool pooler = false;
+  void* ws = nullptr; size_t ws_bytes = 0;
+  uint8_t* stage = nullptr;                 // pixels | last_hidden | pooler staging (graph-owned addresses)
+  size_t pix_bytes = 0, lh_bytes = 0, pool_bytes = 0;
+  int calls = 0;                            // eager calls seen with this key (capture happens on the 2nd)
+  int kernels = 0;                          // kernel nodes in the graph (for sf_launch_count)
+};
+
 struct sf_kv {
   sf_ctx* ctx = nullptr;
   int B = 0, S = 0, cap = 0, seen = 0, horizon = 0;
+  int* d_seen = nullptr;        // device copy of `seen`, advanced by the captured graph itself
+  bool seen_dirty = true;       // host `seen` changed outside a graph launch -> re-upload before the next one
+  bool graphs_disabled = false; // capture failed once: stay on direct launches
+  long graph_launches = 0;      // steps served by a graph replay
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream, which cannot capture)
+  std::vector<StreamGraph> graphs;
   uint8_t* mem = nullptr;
   size_t layer_stride = 0;  // bytes between layers (K then V inside)
   size_t kv_bytes = 0;      // bytes of one K (or V) block
@@ -218,7 +238,8 @@ GemmEpilogue epi_ln(const float* bias, const float* colsum, const float2* stats,
 //   st_in (x_in) -> temporal QKV ; w.stats[0] (after temporal) -> spatial QKV ;
 //   w.stats[1] (after spatial) -> fc1 ; st_out (after the MLP) -> the next layer.
 int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, int B, int T, int S,
-              sf_kv* kv, float* probs, const WsPlan& w, const float2* st_in, int parts_in, float2* st_out) {
+              sf_kv* kv, float* probs, const WsPlan& w, const float2* st_in, int parts_in, float2* st_out,
+              const int* seen_dev = nullptr) {
   const LayerW& lw = c->layers[l];
   const int D = c->D, I = c->I, H = c->H, dt = c->cfg.dtype;
   const long M = static_cast<long>(B) * S * T;
@@ -232,9 +253,9 @@ int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, 
   SF_CHECK(gemm(st, dt, x_in, D, lw.t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
                 epi_ln(lw.t_qkv_b, lw.t_qkv_cs, st_in, parts_in, eps)));
   if (kv) {
-    SF_CHECK(kv_append(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, B * S, H, T, kv->seen));
+    SF_CHECK(kv_append(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, B * S, H, T, kv->seen, seen_dev));
     SF_CHECK(temporal_attention(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, w.ctx, D, B * S, H, T,
-                                kv->seen + T, kv->seen, c->cfg.causal_temporal, scale));
+                                kv->seen + T, kv->seen, c->cfg.causal_temporal, scale, seen_dev));
   } else {
     SF_CHECK(temporal_attention(st, dt, w.qkv, 3 * D, nullptr, nullptr, 0, w.ctx, D, B * S, H, T, T, 0,
                                 c->cfg.causal_temporal, scale));
@@ -280,7 +301,8 @@ int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, 
 }
 
 int run_embed(sf_ctx* c, cudaStream_t st, const void* pixels, int pix_dtype, int B, int T, int Hh, int Ww,
-              int time_off, int time_total, void* x_out, void* patches, float2* stats_out) {
+              int time_off, int time_total, void* x_out, void* patches, float2* stats_out,
+              const int* time_off_dev = nullptr, int time_horizon = 0) {
   const int P = c->cfg.patch_size, C = c->cfg.num_channels, D = c->D, dt = c->cfg.dtype;
   const int S = (Hh / P) * (Ww / P);
   const float* pos = nullptr;
@@ -297,6 +319,7 @@ int run_embed(sf_ctx* c, cudaStream_t st, const void* pixels, int pix_dtype, int
   e.row_map = kRowBTNtoBNT; e.T = T; e.S = S;
   e.pos = pos;
   e.time_emb = c->time_emb; e.time_len = c->cfg.num_frames; e.time_total = time_total; e.time_off = time_off;
+  e.time_off_dev = time_off_dev; e.time_horizon = time_horizon;
   e.stats_out = stats_out;
   return gemm(st, dt, patches, c->Kp, c->patch_w, c->Kp, x_out, D, M, D, c->Kp, e);
 }
@@ -351,7 +374,9 @@ int check_shape(const sf_ctx* c, int B, int T, int Hh, int Ww) {
 
 int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int pix_dtype, int B, int T,
                  int Hh, int Ww, void* last_hidden, void* pooler, void* const* hidden_states,
-                 void* const* attentions, void* ws, size_t ws_bytes) {
+                 void* const* attentions, void* ws, size_t ws_bytes, bool dev_seen = false) {
+  // dev_seen: being captured into a streaming CUDA graph — the kernels take the stream position
+  // from kv->d_seen at run time and the host-side counter is advanced by the caller
   SF_CHECK(check_shape(c, B, T, Hh, Ww));
   SF_CUDA(cudaSetDevice(c->device));
   const int P = c->cfg.patch_size, D = c->D;
@@ -383,16 +408,20 @@ int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int 
   void* cur = hidden_states ? hidden_states[0] : x;
   {
     PhaseScope phase(st, kPhaseEmbed);
-    SF_CHECK(run_embed(c, st, pixels, pix_dtype, B, T, Hh, Ww, time_off, time_total, cur, w.mlp, w.stats[2]));
+    SF_CHECK(run_embed(c, st, pixels, pix_dtype, B, T, Hh, Ww, time_off, time_total, cur, w.mlp, w.stats[2],
+                       dev_seen ? kv->d_seen : nullptr, dev_seen ? kv->horizon : 0));
   }
   const int parts_d = gemm_stats_parts(static_cast<int>(M), D);
   for (int l = 0; l < c->L; ++l) {
     void* nxt = hidden_states ? hidden_states[l + 1] : cur;
     SF_CHECK(run_layer(c, st, l, cur, nxt, B, T, S, kv, attentions ? static_cast<float*>(attentions[l]) : nullptr, w,
-                       w.stats[2], parts_d, w.stats[2]));
+                       w.stats[2], parts_d, w.stats[2], dev_seen ? kv->d_seen : nullptr));
     cur = nxt;
   }
-  if (kv) kv->seen += T;
+  if (kv && !dev_seen) {
+    kv->seen += T;
+    kv->seen_dirty = true;
+  }
   // post_layernorm, written straight in (b,t,n) order == last_hidden_state (…siglip.py:1330-1346)
   PhaseScope phase(st, kPhaseHead);
   SF_CHECK(layernorm(st, c->cfg.dtype, cur, D, c->post_g, c->post_b, c->cfg.layer_norm_eps, last_hidden, D, M,
@@ -405,6 +434,121 @@ int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int 
     SF_CHECK(run_head(c, st, last_hidden, B * T, S, pooler, hb));
   }
   return 0;
+}
+
+// ------------------------------------------------------------------ streaming under a CUDA graph
+// BASELINE config 3 (64 appends of one frame at B=4) is launch-bound when every step re-issues its
+// ~117 kernels from the host (~10 us of CPU per launch incl. two tensor-map encodes).  A streaming
+// step is therefore captured ONCE per (shape, buffers) into a CUDA graph whose kernels read the
+// stream position from a device counter (sf_kv::d_seen) that the graph's last node advances, so the
+// same executable graph replays for every step of every stream; inputs/outputs go through
+// graph-owned staging buffers (two small D2D copies per step).
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+__global__ void add_int_kernel(int* p, int v) {
+  griddep_wait();
+  *p += v;
+}
+
+bool stream_graphs_enabled() {
+  static const bool on = [] { const char* e = getenv("SF_STREAM_GRAPH"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+void destroy_graph(StreamGraph& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (g.stage) cudaFree(g.stage);
+  g.exec = nullptr; g.stage = nullptr;
+}
+
+// returns 1 when the step was served by a graph launch, 0 when the caller must launch directly,
+// < 0 on error
+int try_stream_graph(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int pix_dtype, int B, int T, int Hh,
+                     int Ww, void* last_hidden, void* pooler, void* ws, size_t ws_bytes) {
+  if (!stream_graphs_enabled() || kv->graphs_disabled || prof_enabled() || phase_prof_enabled()) return 0;
+  SF_CHECK(check_shape(c, B, T, Hh, Ww));
+  const int P = c->cfg.patch_size, D = c->D;
+  const int S = (Hh / P) * (Ww / P);
+  if (kv->B != B || kv->S != S || kv->seen + T > kv->cap) return 0;   // the direct path reports the error
+  StreamGraph* g = nullptr;
+  for (auto& it : kv->graphs)
+    if (it.B == B && it.T == T && it.H == Hh && it.W == Ww && it.pix_dtype == pix_dtype && it.pooler == (pooler != nullptr)) g = &it;
+  if (!g) {
+    if (kv->graphs.size() >= 8) return 0;
+    StreamGraph n;
+    n.B = B; n.T = T; n.H = Hh; n.W = Ww; n.pix_dtype = pix_dtype; n.pooler = pooler != nullptr;
+    kv->graphs.push_back(n);
+    g = &kv->graphs.back();
+  }
+  if (g->exec && (g->ws != ws || g->ws_bytes != ws_bytes)) {   // workspace was re-allocated: re-capture
+    cudaGraphExecDestroy(g->exec);
+    g->exec = nullptr;
+    g->calls = 1;
+  }
+  bool just_captured = false;
+  if (!g->exec) {
+    // first call with this key runs eagerly (lazy one-time initialisation inside the launchers
+    // must not happen under capture); the second one captures
+    if (g->calls++ == 0) return 0;
+    SF_CUDA(cudaSetDevice(c->device));
+    if (!g->stage) {
+      const size_t al = 256;
+      g->pix_bytes = (static_cast<size_t>(B) * T * c->cfg.num_channels * Hh * Ww * dtype_size(pix_dtype) + al - 1) / al * al;
+      g->lh_bytes = (static_cast<size_t>(B) * T * S * D * 2 + al - 1) / al * al;
+      g->pool_bytes = (static_cast<size_t>(B) * T * D * 2 + al - 1) / al * al;
+      SF_CUDA(cudaMalloc(&g->stage, g->pix_bytes + g->lh_bytes + g->pool_bytes));
+    }
+    cudaGraph_t graph = nullptr;
+    const uint64_t l0 = launch_count();
+    static const bool debug = getenv("SF_STREAM_GRAPH_DEBUG") != nullptr;
+    auto give_up = [&](const char* what, cudaError_t err, int rc) {
+      if (debug) fprintf(stderr, "[streamformer_b200] stream graph disabled: %s: %s (rc %d: %s)\n", what,
+                         cudaGetErrorString(err), rc, last_error());
+      cudaGetLastError();
+      kv->graphs_disabled = true;
+      return 0;
+    };
+    cudaStream_t cs = kv->cap_stream;
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return give_up("cudaStreamBeginCapture", e, 0);
+    int rc = forward_impl(c, cs, kv, g->stage, pix_dtype, B, T, Hh, Ww, g->stage + g->pix_bytes,
+                          pooler ? g->stage + g->pix_bytes + g->lh_bytes : nullptr, nullptr, nullptr, ws, ws_bytes, true);
+    if (rc == 0) {
+      LaunchCfg lc(dim3(1), dim3(1), 0, cs);
+      if (cudaLaunchKernelEx(&lc.cfg, add_int_kernel, kv->d_seen, T) != cudaSuccess) rc = SF_ERR_CUDA;
+      count_launch();
+    }
+    e = cudaStreamEndCapture(cs, &graph);
+    if (rc != 0 || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      return give_up("capture", e, rc);
+    }
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      g->exec = nullptr;
+      return give_up("cudaGraphInstantiate", e, 0);
+    }
+    g->ws = ws; g->ws_bytes = ws_bytes;
+    g->kernels = static_cast<int>(launch_count() - l0);   // counted while capturing; they run in the launch below
+    just_captured = true;
+  }
+  if (kv->seen_dirty) {
+    set_int_kernel<<<1, 1, 0, st>>>(kv->d_seen, kv->seen);
+    count_launch();
+    kv->seen_dirty = false;
+  }
+  const size_t pix_n = static_cast<size_t>(B) * T * c->cfg.num_channels * Hh * Ww * dtype_size(pix_dtype);
+  SF_CUDA(cudaMemcpyAsync(g->stage, pixels, pix_n, cudaMemcpyDeviceToDevice, st));
+  SF_CUDA(cudaGraphLaunch(g->exec, st));
+  if (!just_captured) count_launch(g->kernels);   // kernels inside the replayed graph
+  SF_CUDA(cudaMemcpyAsync(last_hidden, g->stage + g->pix_bytes, static_cast<size_t>(B) * T * S * D * 2,
+                          cudaMemcpyDeviceToDevice, st));
+  if (pooler)
+    SF_CUDA(cudaMemcpyAsync(pooler, g->stage + g->pix_bytes + g->lh_bytes, static_cast<size_t>(B) * T * D * 2,
+                            cudaMemcpyDeviceToDevice, st));
+  kv->seen += T;
+  kv->graph_launches += 1;
+  return 1;
 }
 
 // ------------------------------------------------------------------ weight binding
@@ -739,28 +883,43 @@ int sf_kv_create(sf_ctx* c, int B, int S, int max_frames, int time_horizon, sf_k
   kv->kv_bytes = static_cast<size_t>(B) * S * c->H * max_frames * 64 * 2;
   kv->layer_stride = 2 * kv->kv_bytes;
   cudaError_t e = cudaMalloc(&kv->mem, kv->layer_stride * c->L);
+  if (e == cudaSuccess) e = cudaMalloc(&kv->d_seen, sizeof(int));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&kv->cap_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     set_error("sf_kv_create: cudaMalloc(%zu bytes) failed: %s", kv->layer_stride * c->L, cudaGetErrorString(e));
+    if (kv->mem) cudaFree(kv->mem);
     delete kv;
     return SF_ERR_CUDA;
   }
   *out = kv;
   return 0;
 }
-int sf_kv_reset(sf_kv* kv) { if (kv) kv->seen = 0; return 0; }
+int sf_kv_reset(sf_kv* kv) {
+  if (kv) { kv->seen = 0; kv->seen_dirty = true; }
+  return 0;
+}
 int sf_kv_destroy(sf_kv* kv) {
   if (!kv) return 0;
+  for (auto& g : kv->graphs) destroy_graph(g);
   if (kv->mem) cudaFree(kv->mem);
+  if (kv->d_seen) cudaFree(kv->d_seen);
+  if (kv->cap_stream) cudaStreamDestroy(kv->cap_stream);
   delete kv;
   return 0;
 }
 int sf_kv_seq_len(const sf_kv* kv) { return kv ? kv->seen : 0; }
 int sf_kv_capacity(const sf_kv* kv) { return kv ? kv->cap : 0; }
+long long sf_kv_graph_launches(const sf_kv* kv) { return kv ? kv->graph_launches : 0; }
 
 int sf_forward_stream(sf_ctx* c, void* stream, sf_kv* kv, const void* pixels, int pixels_dtype, int B, int T_new,
                       int Hh, int Ww, void* last_hidden, void* pooler, void* const* hidden_states, void* workspace,
                       size_t workspace_bytes) {
   if (!c || !kv || !pixels || !last_hidden) { set_error("sf_forward_stream: null argument"); return SF_ERR_INVALID; }
+  if (!hidden_states) {
+    const int served = try_stream_graph(c, static_cast<cudaStream_t>(stream), kv, pixels, pixels_dtype, B, T_new, Hh, Ww,
+                                        last_hidden, pooler, workspace, workspace_bytes);
+    if (served != 0) return served < 0 ? served : 0;
+  }
   return forward_impl(c, static_cast<cudaStream_t>(stream), kv, pixels, pixels_dtype, B, T_new, Hh, Ww, last_hidden,
                       pooler, hidden_states, nullptr, workspace, workspace_bytes);
 }

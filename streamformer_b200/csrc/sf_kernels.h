@@ -34,6 +34,10 @@ struct GemmEpilogue {
   int time_len = 0;                 // rows in the time table (config.num_frames)
   int time_total = 0;               // total frames the table is stretched over (>= time_off+T)
   int time_off = 0;                 // frames already seen (streaming)
+  // streaming under a CUDA graph: time_off = *time_off_dev and
+  // time_total = max(time_horizon, time_off + T), read on the device at run time
+  const int* time_off_dev = nullptr;
+  int time_horizon = 0;
   // LayerNorm folded into this GEMM: A holds the RAW rows x, W was pre-scaled by gamma at bind
   // time, bias is b + W.beta, and the epilogue finishes the normalisation per row:
   //   v = rstd[m] * (acc - mean[m] * ln_colsum[n]) + bias[n]
@@ -79,13 +83,16 @@ int im2col_patches(cudaStream_t stream, int pix_dtype, const void* pixels, int a
 //   Tk == Tq rows per site; else from the cache [site][head][Tcap][64] with Tk valid rows
 //   (the new rows must already be appended).  q row i attends to keys j <= q_off + i when
 //   causal, all Tk keys otherwise.  out[(site*Tq + i), h*64 + d], row stride ld_out.
+//   seen_dev (optional, cache only): device int holding the frames cached before this call; when
+//   given the kernel takes q_off = *seen_dev and Tk = q_off + Tq from it, so one captured CUDA
+//   graph serves every streaming step.
 int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, const void* kcache,
                        const void* vcache, int Tcap, void* out, int ld_out, int sites, int heads,
-                       int Tq, int Tk, int q_off, int causal, float scale);
+                       int Tq, int Tk, int q_off, int causal, float scale, const int* seen_dev = nullptr);
 
 // Append the K and V slices of qkv (rows (site*Tq + i)) into cache[site][head][pos0 + i][64].
 int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
-              int Tcap, int sites, int heads, int Tq, int pos0);
+              int Tcap, int sites, int heads, int Tq, int pos0, const int* seen_dev = nullptr);
 
 // Spatial attention inside each frame: q|k|v column blocks of width heads*64; full (non-causal)
 // softmax over the S keys of the frame.  Row of token n of frame f (same for qkv and out):

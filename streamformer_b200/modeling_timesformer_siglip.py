@@ -160,6 +160,11 @@ class StreamformerKVCache:
     def reset(self) -> None:
         self._engine.lib.sf_kv_reset(self.handle)
 
+    @property
+    def graph_launches(self) -> int:
+        """Steps served by replaying the captured CUDA graph of a streaming step."""
+        return int(self._engine.lib.sf_kv_graph_launches(self.handle))
+
     def __len__(self) -> int:
         return self.get_seq_length()
 

@@ -183,6 +183,37 @@ def test_streaming_matches_twin_golden_and_full_forward(chunks):
     check("stream pooler vs own full", torch.cat(pools, dim=1), full.pooler_output.float().cpu().numpy(), 2 * t["pool"], t["cos"])
 
 
+def test_streaming_graph_replay_is_exact_and_active():
+    """From the second step on a streaming step is replayed from one captured CUDA graph whose kernels
+    read the stream position from a device counter: the replays must equal (bitwise) what direct
+    launches produce, a second stream after reset() must reproduce the first, and an interleaved
+    non-streaming forward (different workspace use) must not disturb the stream."""
+    cfg = O.OracleConfig(num_hidden_layers=2, num_frames=24)
+    w = O.make_weights(cfg, seed=31, style="stress")
+    model = build_model(cfg, w)
+    Tt = 24
+    px = torch.from_numpy(O.make_pixels(2, Tt, cfg, seed=31)).cuda()
+    with torch.no_grad():
+        # direct launches: output_hidden_states=True bypasses the graph path
+        ref_cache = model.new_kv_cache(batch_size=2, max_frames=Tt)
+        ref = [model(px[:, i:i + 1], past_key_values=ref_cache, output_hidden_states=True) for i in range(Tt)]
+        assert ref_cache.graph_launches == 0
+        cache = model.new_kv_cache(batch_size=2, max_frames=Tt)
+        got = []
+        for i in range(Tt):
+            got.append(model(px[:, i:i + 1], past_key_values=cache))
+            if i == 10:
+                model(px[:, :4])          # a one-shot forward in between reuses the same workspace
+        assert cache.graph_launches >= Tt - 3, "streaming steps were not served by the CUDA graph"
+        for i in range(Tt):
+            assert torch.equal(got[i].last_hidden_state, ref[i].last_hidden_state), f"step {i}"
+            assert torch.equal(got[i].pooler_output, ref[i].pooler_output), f"step {i} pooler"
+        cache.reset()
+        again = [model(px[:, i:i + 1], past_key_values=cache).last_hidden_state for i in range(Tt)]
+        for i in range(Tt):
+            assert torch.equal(again[i], ref[i].last_hidden_state), f"second stream, step {i}"
+
+
 def test_streaming_cache_overflow_and_reset():
     from streamformer_b200 import _native as N
     cfg = O.OracleConfig(num_hidden_layers=1)

@@ -87,6 +87,17 @@ def main():
         gemm_case("fc2 (bias+res+stats)", D, I, residual=True, stats=True)
         gemm_case("head kv (bias)", 2 * D, D)
 
+    if a.only and "k64" in a.only:
+        # K = 64 (one K block): the main loop is negligible, so these time the EPILOGUE + store path
+        gemm_case("k64 N=2304 (bias)", 3 * D, 64)
+        gemm_case("k64 N=2304 (folded LN)", 3 * D, 64, ln=True)
+        gemm_case("k64 N=768 (bias)", D, 64)
+        gemm_case("k64 N=768 (bias+res+gate+stats)", D, 64, residual=True, gate=True, stats=True)
+        gemm_case("k64 N=3072 (bias)", I, 64)
+        gemm_case("k64 N=3072 (folded LN+gelu)", I, 64, act=1, ln=True)
+        gemm_case("k256 N=2304 (bias)", 3 * D, 256)
+        gemm_case("k1536 N=2304 (bias)", 3 * D, 1536)
+
     if a.only and "cublas" in a.only:
         # library reference on the same shapes (context only: cuBLAS is not on the product path)
         for name, Nn, K in (("qkv", 3 * D, D), ("proj", D, D), ("fc1", I, D), ("fc2", D, I)):
@@ -118,6 +129,8 @@ def main():
         res["spatial_attention"] = {"ms": round(ms, 4), "tflops": round(fl / (ms * 1e-3) / 1e12, 1),
                                     "gbs": round(8.0 * M * D / (ms * 1e-3) / 1e9, 1)}
         print(f"spatial attention: {ms*1e3:8.1f} us  {fl/(ms*1e-3)/1e12:6.1f} TFLOP/s  {8.0*M*D/(ms*1e-3)/1e9:7.1f} GB/s", flush=True)
+        ms1 = timeit(lambda i: ops.spatial_attention(qs[i], a.B * a.T, 12, S, 0.125, T_inner=1), nrot)
+        print(f"spatial attention (frames contiguous, T_inner=1): {ms1*1e3:8.1f} us", flush=True)
         ms = timeit(lambda i: ops.temporal_attention(qs[i], a.B * S, 12, a.T, True, 0.125), nrot)
         res["temporal_attention"] = {"ms": round(ms, 4), "gbs": round(8.0 * M * D / (ms * 1e-3) / 1e9, 1)}
         print(f"temporal attention: {ms*1e3:8.1f} us  {8.0*M*D/(ms*1e-3)/1e9:7.1f} GB/s", flush=True)
