@@ -338,17 +338,17 @@ def run_ours(args):
         # layer (temporal QKV + causal attention + out-proj.temporal_dense + gate, spatial QKV +
         # attention + out-proj; SURVEY 8d: 35.34 GFLOP per clip and layer algorithmic, un-folded)
         ab = phases["attention_block"]
-        ab_ms = ab["ms"] / max(ab["count"], 1)
+        ab_ms = ab["ms"] / (args.layers * PK)      # per layer (a layer contributes two timed spans in this mode)
         ab_algo = O.attention_block_flops_per_clip(ocfg, T) * B
         ab_exec = ab_algo - (2.0 * B * T * S * D * D if not args.no_fold else 0.0)
         attention_block = {
-            "ms_per_layer": ab_ms, "layers_timed": ab["count"],
+            "ms_per_layer": ab_ms, "layers_timed": args.layers * PK,
             "algorithmic_gflop_per_layer": ab_algo / 1e9, "executed_gflop_per_layer": ab_exec / 1e9,
             "algorithmic_tflops": ab_algo / (ab_ms * 1e-3) / 1e12, "executed_tflops": ab_exec / (ab_ms * 1e-3) / 1e12,
             "frac_of_burst_peak_algorithmic": ab_algo / (ab_ms * 1e-3) / 1e12 / peaks["burst"],
             "frac_of_burst_peak_executed": ab_exec / (ab_ms * 1e-3) / 1e12 / peaks["burst"],
             "frac_of_sustained_peak_executed": ab_exec / (ab_ms * 1e-3) / 1e12 / peaks["sustained"],
-            "mlp_ms_per_layer": phases["mlp"]["ms"] / max(phases["mlp"]["count"], 1),
+            "mlp_ms_per_layer": phases["mlp"]["ms"] / (args.layers * PK),
             "embed_ms": phases["embed"]["ms"] / max(phases["embed"]["count"], 1),
             "head_ms": phases["head"]["ms"] / max(phases["head"]["count"], 1),
             "how": "CUDA events around the block of every layer (sf_profile mode 2), kernels back to back with PDL",

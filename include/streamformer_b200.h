@@ -78,6 +78,11 @@ const char* sf_version(void);
 /* kernels launched by this library since it was loaded */
 uint64_t sf_launch_count(void);
 
+/* Library-wide switches.  "gemm_chain": 1 runs GEMMs that follow each other over the same rows
+ * (out-proj -> fc1 -> fc2 -> next QKV ...) as one persistent launch with in-kernel row dependencies,
+ * 0 one launch per GEMM, -1 the default (SF_GEMM_CHAIN environment variable, off). */
+int sf_set_option(const char* name, int value);
+
 /* In-situ profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.
  * sf_profile_collect synchronises the device and returns, per kernel class (0 gemm, 1 layernorm,
  * 2 im2col, 3 temporal attention, 4 spatial attention, 5 pooling attention, 6 kv append, 7 other),

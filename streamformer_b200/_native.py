@@ -19,7 +19,7 @@ SF_ROW_IDENTITY, SF_ROW_BTN_TO_BNT, SF_ROW_BNT_TO_BTN = 0, 1, 2
 
 # every symbol include/streamformer_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
-    "sf_last_error", "sf_version", "sf_launch_count", "sf_profile", "sf_profile_collect", "sf_profile_collect_phases",
+    "sf_last_error", "sf_version", "sf_launch_count", "sf_set_option", "sf_profile", "sf_profile_collect", "sf_profile_collect_phases",
     "sf_create", "sf_destroy", "sf_bind_weights", "sf_set_pos_embed",
     "sf_workspace_bytes", "sf_forward",
     "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_kv_graph_launches", "sf_forward_stream",
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     lib.sf_last_error.restype = C.c_char_p
     lib.sf_version.restype = C.c_char_p
     lib.sf_launch_count.restype = C.c_uint64
+    lib.sf_set_option.argtypes = [C.c_char_p, i]
     lib.sf_profile.argtypes = [i]
     lib.sf_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_longlong), i]
@@ -120,6 +121,10 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().sf_last_error().decode("utf-8", "replace")
         raise NativeError(f"{what or 'streamformer_b200'} failed (status {rc}): {msg}")
+
+
+def set_option(name: str, value: int) -> None:
+    check(load().sf_set_option(name.encode(), int(value)), "sf_set_option")
 
 
 def launch_count() -> int:

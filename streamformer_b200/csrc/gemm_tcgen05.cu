@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "sf_kernels.h"
 #include "sf_ptx.cuh"
@@ -30,6 +31,7 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;             // 64 x 2 B = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
+constexpr int kChainMaxPhases = 4;
 
 // epilogue flavours (compile-time: keeps each kernel's code small and branch-free)
 enum EpiMode : int { kEpiBias = 0, kEpiAct = 1, kEpiResidual = 2, kEpiEmbed = 3 };
@@ -1157,6 +1159,510 @@ int dispatch_epilogue(cudaStream_t stream, int dtype, const void* A, int lda, co
   return dispatch_shape<T, kEpiBias>(stream, dtype, A, lda, W, ldw, p);
 }
 
+
+// =====================================================================================  GEMM chains
+// Several dependent GEMMs over the SAME rows (attention out-proj -> fc1 -> fc2 -> the next layer's
+// QKV, ...) as ONE persistent launch.  Each stand-alone GEMM pays ~12 us of pipeline fill (first
+// operand fetch + a whole main loop before any epilogue work exists) and drain (the last tile's
+// epilogue with idle tensor cores) — 18 % of a K = 768 GEMM, six times per layer.  In a chain the
+// tiles of all phases form one sequence dealt round-robin to the CTA pairs: the drain of phase p
+// overlaps the fill of phase p+1.  Dependencies are row-local — tile (p, m, n) needs every tile
+// (p-1, m, *) — and are tracked with one counter per (phase, M tile) in global memory: epilogue
+// warps release-increment it once their TMA stores have completed, the TMA producer / aux warp /
+// residual prefetch of a dependent tile acquire-spin on it (normally already satisfied: the
+// producing tiles are ~num_workers positions earlier in the sequence).  All CTAs are co-resident
+// (persistent grid <= SM count) and every worker walks the sequence in order, so the earliest
+// unfinished tile can always run: no deadlock.  The last CTA to leave zeroes the counters again, so
+// every launch starts from a clean set without host-side state (safe under CUDA-graph replay).
+
+struct ChainMaps {
+  CUtensorMap a[kChainMaxPhases], b[kChainMaxPhases], out[kChainMaxPhases], res[kChainMaxPhases];
+};
+struct ChainPhase {
+  int N, K, n_tiles, k_blocks, tile_begin;
+  int mode;            // kEpiBias (bias / folded LN), kEpiAct, kEpiResidual
+  int signal;          // a later phase consumes this one's rows
+  uint32_t expected;   // arrivals per (phase, M tile) counter and launch: n_tiles * 2 CTAs * epilogue warps
+  void* out;
+  int ldo;
+  GemmEpilogue epi;
+};
+struct ChainParams {
+  int M, m_tiles, num_phases, total_tiles;
+  uint32_t* done;      // [kChainMaxPhases][m_tiles] arrival counters + one CTA-exit counter, all zero between launches
+  ChainPhase ph[kChainMaxPhases];
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// position of one worker in the tile sequence of a chain
+struct ChainWalk {
+  int g, step, p;
+  __device__ ChainWalk(int worker, int workers) : g(worker), step(workers), p(0) {}
+  __device__ bool valid(const ChainParams& c) const { return g < c.total_tiles; }
+  __device__ void locate(const ChainParams& c) {
+    while (p + 1 < c.num_phases && g >= c.ph[p + 1].tile_begin) ++p;
+  }
+  __device__ int m_tile(const ChainParams& c) const { return (g - c.ph[p].tile_begin) / c.ph[p].n_tiles; }
+  __device__ int n_tile(const ChainParams& c) const { return (g - c.ph[p].tile_begin) % c.ph[p].n_tiles; }
+  __device__ void next(const ChainParams& c) { g += step; locate(c); }
+};
+
+// rows of M tile `m_tile` written by phase p-1 are complete and visible (to generic and async proxy)
+__device__ __forceinline__ void chain_wait(const ChainParams& c, int p, int m_tile) {
+  if (p == 0) return;
+  const uint32_t* ctr = c.done + (p - 1) * c.m_tiles + m_tile;
+  const uint32_t target = c.ph[p - 1].expected;
+  while (ld_acquire_gpu(ctr) < target) __nanosleep(40);
+  // no proxy fence: the rows were complete in L2 (bulk-group completion) before the producer's
+  // release, and TMA / ld.global.cg reads are served from L2
+}
+
+template <typename T, int EW>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
+gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams cp) {
+  constexpr int BN = 256, CG = 2;
+  using L = SmemLayout<BN, CG, EW, true>;
+  constexpr int kTileM = kBM * CG;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + L::kSlots;
+  uint64_t* tmem_full = empty_bar + L::kSlots;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* aux_full = tmem_empty + 2;
+  uint64_t* aux_empty = aux_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + 2);
+  uint64_t* res_bar = aux_empty + 3;
+  static_assert((2 * L::kSlots + 8 + 1 + 3 * EW) * 8 <= L::kBarBytes, "chain barrier area overflow");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int worker = blockIdx.x / CG;
+  const int num_workers = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    for (int q = 0; q < cp.num_phases; ++q) {
+      tma_prefetch_desc(&maps.a[q]);
+      tma_prefetch_desc(&maps.b[q]);
+      tma_prefetch_desc(&maps.out[q]);
+      if (cp.ph[q].mode == kEpiResidual) tma_prefetch_desc(&maps.res[q]);
+    }
+    for (int s = 0; s < L::kSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 3 * EW; ++i) mbar_init(&res_bar[i], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], EW * CG);
+      mbar_init(&aux_full[a], 1);
+      mbar_init(&aux_empty[a], EW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_slot, 2 * BN);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch_dependents();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (every CTA)
+    if (elect_one_sync()) {
+      int slot = 0;
+      uint32_t phase = 0;
+      auto ring_load = [&](const CUtensorMap* tm, int c0, int c1) {
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        if (leader) mbar_arrive_expect_tx(&full_bar[slot], 2 * L::kSlotBytes);
+        tma_load_2d_cg2(smem + slot * L::kSlotBytes, tm, &full_bar[slot], c0, c1);
+        if (++slot == L::kSlots) { slot = 0; phase ^= 1; }
+      };
+      // the dependency counter of the NEXT tile is requested while this tile's operands stream in, so
+      // the (normally satisfied) check costs no round trip on the critical path
+      uint32_t pre_val = 0;
+      bool pre_have = false;
+      for (ChainWalk w(worker, num_workers); w.valid(cp); w.next(cp)) {
+        const int q = w.p;
+        const int mt = w.m_tile(cp);
+        const int m0 = mt * kTileM + static_cast<int>(cta_rank) * kBM;
+        const int n0 = w.n_tile(cp) * BN + static_cast<int>(cta_rank) * (BN / CG);
+        // the A rows come from the previous phase
+        if (q > 0 && !(pre_have && pre_val >= cp.ph[q - 1].expected)) chain_wait(cp, q, mt);
+        {
+          ChainWalk nx = w;
+          nx.next(cp);
+          pre_have = false;
+          if (nx.valid(cp) && nx.p > 0) {
+            pre_val = ld_acquire_gpu(cp.done + (nx.p - 1) * cp.m_tiles + nx.m_tile(cp));
+            pre_have = true;
+          }
+        }
+        const int kbs = cp.ph[q].k_blocks;
+        for (int kb = 0; kb < kbs; ++kb) {
+          ring_load(&maps.a[q], kb * kBK, m0);
+          ring_load(&maps.b[q], kb * kBK, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, UmmaFmt<T>::value);
+    if (leader && elect_one_sync()) {
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (ChainWalk w(worker, num_workers); w.valid(cp); w.next(cp), ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const int kbs = cp.ph[w.p].k_blocks;
+        for (int kb = 0; kb < kbs; ++kb) {
+          mbar_wait(&full_bar[slot], phase);
+          const int a_slot = slot;
+          if (++slot == L::kSlots) { slot = 0; phase ^= 1; }
+          mbar_wait(&full_bar[slot], phase);
+          const int b_slot = slot;
+          if (++slot == L::kSlots) { slot = 0; phase ^= 1; }
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128_kmajor(smem_u32(smem + a_slot * L::kSlotBytes));
+          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(smem + b_slot * L::kSlotBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_cg2_mc(&empty_bar[a_slot], 0x3);
+          umma_commit_cg2_mc(&empty_bar[b_slot], 0x3);
+        }
+        umma_commit_cg2_mc(&tmem_full[acc], 0x3);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ aux warp (one tile ahead)
+    int it = 0;
+    for (ChainWalk w(worker, num_workers); w.valid(cp); w.next(cp), ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const ChainPhase& P = cp.ph[w.p];
+      const GemmEpilogue& e = P.epi;
+      const bool ln = P.mode != kEpiResidual && e.ln_stats != nullptr;
+      const int mt = w.m_tile(cp);
+      const int m0 = mt * kTileM + static_cast<int>(cta_rank) * kBM;
+      const int n0 = w.n_tile(cp) * BN;
+      const float inv_k = 1.0f / static_cast<float>(P.K);
+      constexpr int kVec = BN / 4 / 32;
+      float4 b4[kVec], c4[kVec];
+#pragma unroll
+      for (int v = 0; v < kVec; ++v) {
+        const int col = n0 + (v * 32 + lane) * 4;
+        b4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        c4[v] = b4[v];
+        if (col < P.N) {
+          if (e.bias) b4[v] = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+          if (ln) c4[v] = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + col));
+        }
+      }
+      float s1x[kBM / 32], s2x[kBM / 32];
+      if (ln) {
+        chain_wait(cp, w.p, mt);                     // the row statistics come from the previous phase
+        // two row groups per round trip (the statistics were written inside this launch: coherent loads)
+        constexpr int kParts = 12;                   // partials per batch (N = 768 producers: 12 x 64 columns)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float a1[2] = {0.f, 0.f}, a2[2] = {0.f, 0.f};
+          for (int q = 0; q < e.ln_parts; q += kParts) {
+            float2 t[2][kParts];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int m = m0 + (half * 2 + rr) * 32 + lane;
+#pragma unroll
+              for (int u = 0; u < kParts; ++u) {
+                t[rr][u] = make_float2(0.f, 0.f);
+                if (q + u < e.ln_parts && m < cp.M) t[rr][u] = __ldcg(e.ln_stats + static_cast<long>(q + u) * cp.M + m);
+              }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+              for (int u = 0; u < kParts; ++u) {
+                a1[rr] += t[rr][u].x;
+                a2[rr] += t[rr][u].y;
+              }
+            }
+          }
+          s1x[half * 2] = a1[0]; s2x[half * 2] = a2[0];
+          s1x[half * 2 + 1] = a1[1]; s2x[half * 2 + 1] = a2[1];
+        }
+      }
+      mbar_wait(&aux_empty[st], ph ^ 1);
+      const uint32_t aux_u = smem_u32(smem + L::kAuxOffset + st * L::kAuxBytesPerStage);
+#pragma unroll
+      for (int v = 0; v < kVec; ++v) {
+        sts128f(aux_u + L::kAuxBias + (v * 32 + lane) * 16, b4[v]);
+        sts128f(aux_u + L::kAuxColsum + (v * 32 + lane) * 16, c4[v]);
+      }
+      if (ln) {
+#pragma unroll
+        for (int rr = 0; rr < kBM / 32; ++rr) {
+          const float mean = s1x[rr] * inv_k;
+          const float var = fmaxf(fmaf(s2x[rr], inv_k, -mean * mean), 0.f);
+          const float rstd = rsqrtf(var + e.ln_eps);
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(aux_u + L::kAuxRows + (rr * 32 + lane) * 8), "f"(-mean), "f"(rstd)
+                       : "memory");
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aux_full[st]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps (TMA-store path)
+    const int ew = warp - 4;
+    const int quarter = warp & 3;
+    const int colgrp = ew >> 2;
+    constexpr int kColsPerWarp = BN / (EW / 4);     // 64 (16 warps) / 128 (8 warps)
+    constexpr int kCW = L::kChunkCols;              // 16 / 32
+    constexpr int kChunks = kColsPerWarp / kCW;     // 4
+    constexpr int kRowBytes = kCW * 2;
+    constexpr int kBufBytes = L::kStageBufBytes;
+    constexpr int kC16 = kRowBytes / 16;
+    uint8_t* stg = smem + L::kStagingOffset + ew * (3 * kBufBytes);
+    const uint32_t stg_u = smem_u32(stg);
+    uint64_t* rbar = res_bar + ew * 3;
+    const uint32_t swz = (static_cast<uint32_t>(lane) / (128 / kRowBytes)) & (kC16 - 1);
+    const uint32_t my_row_u = static_cast<uint32_t>(lane) * kRowBytes;
+    uint32_t f = 0;          // chunks processed so far: staging buffer f % 3
+    uint32_t rpar = 0;       // bit b: parity of the next residual arrival in buffer b
+    // residual look-ahead (lane 0): the chunk two ahead of the one being processed
+    ChainWalk wl(worker, num_workers);
+    int lc = 0;
+    uint32_t lf = 0;
+    // Advances the look-ahead by one chunk (requesting its residual box if it belongs to a residual
+    // phase).  With block == false it gives up (returns false) when the chunk's tile still waits for
+    // an earlier phase: that phase may need THIS warp's current tile (short chains: the producing
+    // tile can be exactly one round earlier on the same worker), so spinning here would deadlock.
+    auto advance_res = [&](bool block) -> bool {
+      if (wl.valid(cp)) {
+        const ChainPhase& LP = cp.ph[wl.p];
+        if (LP.mode == kEpiResidual) {
+          const int mt = wl.m_tile(cp);
+          if (lc == 0 && wl.p > 0) {
+            const uint32_t* ctr = cp.done + (wl.p - 1) * cp.m_tiles + mt;
+            if (!block && ld_acquire_gpu(ctr) < cp.ph[wl.p - 1].expected) return false;
+            chain_wait(cp, wl.p, mt);
+          }
+          const int lrow = mt * kTileM + static_cast<int>(cta_rank) * kBM + quarter * 32;
+          const int lcol = wl.n_tile(cp) * BN + colgrp * kColsPerWarp + lc * kCW;
+          const uint32_t b = lf % 3;
+          mbar_arrive_expect_tx(&rbar[b], kBufBytes);
+          tma_load_2d(stg + b * kBufBytes, &maps.res[wl.p], &rbar[b], lcol, lrow);
+        }
+        if (++lc == kChunks) { lc = 0; wl.next(cp); }
+      }
+      ++lf;
+      return true;
+    };
+    if (lane == 0) { while (lf < 2 && advance_res(false)) {} }
+    // Completion of a tile is signalled lazily, while the NEXT tile's second chunk is processed (its
+    // TMA stores have landed by then, so nothing stalls) — unless the next accumulator is not ready:
+    // then the wait is free, and it might even be this very signal the next tile depends on.
+    uint32_t* pend_ctr = nullptr;
+    auto flush_signal = [&]() {
+      if (pend_ctr != nullptr) {
+        if (lane == 0) {
+          tma_store_wait<0>();
+          __threadfence();
+          red_release_gpu_add(pend_ctr, 1u);
+        }
+        pend_ctr = nullptr;
+      }
+    };
+    int it = 0;
+    for (ChainWalk w(worker, num_workers); w.valid(cp); w.next(cp), ++it) {
+      const ChainPhase& P = cp.ph[w.p];
+      const GemmEpilogue& e = P.epi;
+      const int mode = P.mode;
+      const bool ln = mode != kEpiResidual && e.ln_stats != nullptr;
+      const bool want_stats = mode == kEpiResidual && e.stats_out != nullptr;
+      const float gscale = e.gate ? tanhf(__ldg(e.gate)) : 1.0f;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int mt = w.m_tile(cp);
+      const int m0 = mt * kTileM + static_cast<int>(cta_rank) * kBM;
+      const int n0 = w.n_tile(cp) * BN;
+      const int row0 = m0 + quarter * 32;
+      const int m = row0 + lane;
+      const int wcol0 = n0 + colgrp * kColsPerWarp;
+      const uint32_t aux_u = smem_u32(smem + L::kAuxOffset + acc * L::kAuxBytesPerStage);
+      const uint32_t bias_u = aux_u + L::kAuxBias + colgrp * kColsPerWarp * 4;
+      const uint32_t csum_u = aux_u + L::kAuxColsum + colgrp * kColsPerWarp * 4;
+      if (pend_ctr != nullptr) {
+        // about to block on this tile's aux stage / accumulator: if either is not there yet, publish
+        // the previous tile first (the wait is free, and this tile may be waiting for that signal)
+        const bool r = mbar_try_wait(&aux_full[acc], acc_phase) && mbar_try_wait(&tmem_full[acc], acc_phase);
+        if (!__shfl_sync(0xffffffffu, r ? 1u : 0u, 0)) flush_signal();
+      }
+      mbar_wait(&aux_full[acc], acc_phase);
+      float nmean = 0.f, rstd = 1.f;
+      if (ln) {
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(nmean), "=f"(rstd)
+                     : "r"(aux_u + L::kAuxRows + (quarter * 32 + lane) * 8));
+      }
+      float st1 = 0.f, st2 = 0.f;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + colgrp * kColsPerWarp;
+      uint32_t raw[2][kCW];
+      auto tmem_fetch = [&](int c, uint32_t (&dst)[kCW]) {
+        if constexpr (kCW == 32) tmem_ld_32x32b_x32(t_base + c * kCW, dst);
+        else tmem_ld_32x32b_x16(t_base + c * kCW, dst);
+      };
+      tmem_fetch(0, raw[0]);
+#pragma unroll 1
+      for (int cpair = 0; cpair < kChunks / 2; ++cpair) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = cpair * 2 + h;
+          const int col0 = wcol0 + c * kCW;
+          tmem_ld_wait();
+          if (c + 1 < kChunks) {
+            tmem_fetch(c + 1, raw[h ^ 1]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+          }
+          if (c == 1 && pend_ctr != nullptr) {
+            // only this tile's first store may still be in flight: the previous tile's have landed
+            if (lane == 0) {
+              tma_store_wait<1>();
+              __threadfence();
+              red_release_gpu_add(pend_ctr, 1u);
+            }
+            pend_ctr = nullptr;
+          }
+          const uint32_t buf = f % 3;
+          const uint32_t buf_u = stg_u + buf * kBufBytes;
+          uint32_t rb[kCW / 2];
+          if (mode == kEpiResidual) {
+            // this tile's dependencies are satisfied (its accumulator exists): catch up if the
+            // look-ahead had to hold back
+            if (lane == 0) { while (lf <= f) advance_res(true); }
+            mbar_wait(&rbar[buf], (rpar >> buf) & 1);
+            rpar ^= 1u << buf;
+#pragma unroll
+            for (int q = 0; q < kC16; ++q) lds128u(buf_u + my_row_u + ((static_cast<uint32_t>(q) ^ swz) << 4), &rb[q * 4]);
+          }
+          uint32_t ob[kCW / 2];
+#pragma unroll
+          for (int g = 0; g < kCW / 8; ++g) {
+            float vv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = __uint_as_float(raw[h][g * 8 + j]);
+            const float4 b0 = lds128f(bias_u + (c * kCW + g * 8) * 4);
+            const float4 b1 = lds128f(bias_u + (c * kCW + g * 8 + 4) * 4);
+            if (ln) {
+              const float4 c0 = lds128f(csum_u + (c * kCW + g * 8) * 4);
+              const float4 c1 = lds128f(csum_u + (c * kCW + g * 8 + 4) * 4);
+              vv[0] = fmaf(rstd, fmaf(nmean, c0.x, vv[0]), b0.x); vv[1] = fmaf(rstd, fmaf(nmean, c0.y, vv[1]), b0.y);
+              vv[2] = fmaf(rstd, fmaf(nmean, c0.z, vv[2]), b0.z); vv[3] = fmaf(rstd, fmaf(nmean, c0.w, vv[3]), b0.w);
+              vv[4] = fmaf(rstd, fmaf(nmean, c1.x, vv[4]), b1.x); vv[5] = fmaf(rstd, fmaf(nmean, c1.y, vv[5]), b1.y);
+              vv[6] = fmaf(rstd, fmaf(nmean, c1.z, vv[6]), b1.z); vv[7] = fmaf(rstd, fmaf(nmean, c1.w, vv[7]), b1.w);
+            } else {
+              vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+              vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+            }
+            if (mode == kEpiAct) {
+              if (e.act == kActGeluErf) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
+              }
+            } else if (mode == kEpiResidual) {
+              const uint32_t* rq = &rb[g * 4];
+              const float2 r0 = Pack2<T>::unpack(rq[0]), r1 = Pack2<T>::unpack(rq[1]);
+              const float2 r2 = Pack2<T>::unpack(rq[2]), r3 = Pack2<T>::unpack(rq[3]);
+              vv[0] = fmaf(gscale, vv[0], r0.x); vv[1] = fmaf(gscale, vv[1], r0.y);
+              vv[2] = fmaf(gscale, vv[2], r1.x); vv[3] = fmaf(gscale, vv[3], r1.y);
+              vv[4] = fmaf(gscale, vv[4], r2.x); vv[5] = fmaf(gscale, vv[5], r2.y);
+              vv[6] = fmaf(gscale, vv[6], r3.x); vv[7] = fmaf(gscale, vv[7], r3.y);
+            }
+            uint32_t* oq = &ob[g * 4];
+            oq[0] = Pack2<T>::pack(vv[0], vv[1]); oq[1] = Pack2<T>::pack(vv[2], vv[3]);
+            oq[2] = Pack2<T>::pack(vv[4], vv[5]); oq[3] = Pack2<T>::pack(vv[6], vv[7]);
+            if (want_stats) {
+              const float2 q0 = Pack2<T>::unpack(oq[0]), q1 = Pack2<T>::unpack(oq[1]);
+              const float2 q2 = Pack2<T>::unpack(oq[2]), q3 = Pack2<T>::unpack(oq[3]);
+              st1 += ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+              st2 = fmaf(q0.x, q0.x, fmaf(q0.y, q0.y, fmaf(q1.x, q1.x, fmaf(q1.y, q1.y, st2))));
+              st2 = fmaf(q2.x, q2.x, fmaf(q2.y, q2.y, fmaf(q3.x, q3.x, fmaf(q3.y, q3.y, st2))));
+            }
+          }
+          // staging buffer hand-over: (residual in ->) output out
+          if (lane == 0) tma_store_wait_read<2>();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < kC16; ++q) sts128u(buf_u + my_row_u + ((static_cast<uint32_t>(q) ^ swz) << 4), &ob[q * 4]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (row0 < cp.M) tma_store_2d(&maps.out[w.p], stg + buf * kBufBytes, col0, row0);
+            tma_store_commit();
+            tma_store_wait_read<1>();
+            while (lf < f + 3 && advance_res(false)) {}     // residual boxes of chunks f + 1, f + 2
+          }
+          ++f;
+        }
+      }
+      if (want_stats && m < cp.M)
+        e.stats_out[static_cast<long>(wcol0 / kColsPerWarp) * cp.M + m] = make_float2(st1, st2);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aux_empty[acc]);
+      // this warp's part of the tile is complete once its TMA stores have landed; the statistics
+      // stores of all lanes are ordered before lane 0's release by the __syncwarp above
+      if (P.signal) pend_ctr = cp.done + w.p * cp.m_tiles + mt;
+    }
+    flush_signal();
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 2 * BN);
+  }
+  // every wait of this CTA is behind it: count it out; the last CTA of the grid re-arms the counters
+  if (threadIdx.x == 0) {
+    uint32_t* exit_ctr = cp.done + kChainMaxPhases * cp.m_tiles;
+    __threadfence();
+    if (atomicAdd(exit_ctr, 1u) == gridDim.x - 1) {
+      for (int i = 0; i < kChainMaxPhases * cp.m_tiles; ++i) cp.done[i] = 0u;
+      *exit_ctr = 0u;
+      __threadfence();
+    }
+  }
+}
+
 }  // namespace
 
 int gemm_stats_parts(int M, int N) {
@@ -1166,6 +1672,125 @@ int gemm_stats_parts(int M, int N) {
   const int bn = pick_shape(M, N) == 2 ? 128 : 256;
   const int cols_per_part = bn / (ew / 4);
   return (N + cols_per_part - 1) / cols_per_part;
+}
+
+// Chains are opt-in (sf_set_option("gemm_chain", 1) or SF_GEMM_CHAIN=1): correct and tested, but on
+// B200 the chained schedule currently measures SLOWER than one launch per GEMM (7.43 vs 6.52 ms per
+// cfg2 step), so the default stays one launch per GEMM.
+int g_chain_override = -1;
+bool gemm_chain_supported(int dtype, const GemmCall* calls, int n) {
+  static const bool env_on = env_int("SF_GEMM_CHAIN", 0) != 0;
+  const bool on = g_chain_override >= 0 ? g_chain_override != 0 : env_on;
+  if (!on || n < 2 || n > kChainMaxPhases || (dtype != kBF16 && dtype != kF16)) return false;
+  for (int i = 0; i < n; ++i) {
+    const GemmCall& c = calls[i];
+    const GemmEpilogue& e = c.epi;
+    if (c.M != calls[0].M || c.M <= 0 || c.N <= 0 || c.K <= 0) return false;
+    if ((c.K % 8) || (c.N % 8) || (c.lda % 8) || (c.ldw % 8) || (c.ldo % 8) || (e.residual && (e.ldr % 8))) return false;
+    if (pick_shape(c.M, c.N) != 0) return false;                       // CTA-pair 256 x 256 tiles only
+    if (e.row_map != kRowIdentity || e.pos || e.time_emb) return false;
+    if (e.residual && (e.act != kActNone || e.ln_stats)) return false;
+    if (e.stats_out && !e.residual) return false;
+    if (e.gate && !e.residual) return false;
+  }
+  return true;
+}
+
+// 16 epilogue warps (64 columns per row-statistics partial) when a phase has an activation (the
+// GELU epilogue needs four warps per scheduler), else 8 (128 columns per partial)
+int chain_epi_warps(const GemmCall* calls, int n) {
+  for (int i = 0; i < n; ++i)
+    if (calls[i].epi.act != kActNone) return 16;
+  return 8;
+}
+void set_gemm_chain(int on) { g_chain_override = on; }
+int gemm_chain_stats_parts(const GemmCall* calls, int n, int N) {
+  const int cols = 256 / (chain_epi_warps(calls, n) / 4);
+  return (N + cols - 1) / cols;
+}
+
+size_t gemm_chain_counter_bytes(int M) {
+  return (static_cast<size_t>(kChainMaxPhases) * ((M + 2 * kBM - 1) / (2 * kBM)) + 1) * sizeof(uint32_t);
+}
+
+template <int EW>
+int launch_chain(cudaStream_t stream, int dtype, const GemmCall* calls, int n, void* counters);
+
+int gemm_chain(cudaStream_t stream, int dtype, const GemmCall* calls, int n, void* counters) {
+  if (!gemm_chain_supported(dtype, calls, n)) { set_error("gemm_chain: unsupported chain"); return -1; }
+  if (chain_epi_warps(calls, n) == 16) return launch_chain<16>(stream, dtype, calls, n, counters);
+  return launch_chain<8>(stream, dtype, calls, n, counters);
+}
+
+template <int EW>
+int launch_chain(cudaStream_t stream, int dtype, const GemmCall* calls, int n, void* counters) {
+  using L = SmemLayout<256, 2, EW, true>;
+  ChainMaps maps;
+  ChainParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.M = calls[0].M;
+  cp.m_tiles = (cp.M + 2 * kBM - 1) / (2 * kBM);
+  cp.num_phases = n;
+  cp.done = static_cast<uint32_t*>(counters);
+  int tiles = 0;
+  double flops = 0.0, bytes = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const GemmCall& c = calls[i];
+    ChainPhase& P = cp.ph[i];
+    P.N = c.N; P.K = c.K;
+    P.n_tiles = (c.N + 255) / 256;
+    P.k_blocks = (c.K + kBK - 1) / kBK;
+    P.tile_begin = tiles;
+    tiles += cp.m_tiles * P.n_tiles;
+    P.mode = c.epi.residual ? kEpiResidual : (c.epi.act != kActNone ? kEpiAct : kEpiBias);
+    P.signal = i + 1 < n ? 1 : 0;
+    P.expected = static_cast<uint32_t>(P.n_tiles) * 2u * EW;
+    P.out = c.out; P.ldo = c.ldo;
+    P.epi = c.epi;
+    int rc = make_operand_map(&maps.a[i], dtype, c.A, c.M, c.K, c.lda, kBM);
+    if (rc) return rc;
+    rc = make_operand_map(&maps.b[i], dtype, c.W, c.N, c.K, c.ldw, 128);
+    if (rc) return rc;
+    rc = make_io_map(&maps.out[i], dtype, c.out, c.M, c.N, c.ldo, L::kChunkCols);
+    if (rc) return rc;
+    if (c.epi.residual) {
+      rc = make_io_map(&maps.res[i], dtype, c.epi.residual, c.M, c.N, c.epi.ldr, L::kChunkCols);
+      if (rc) return rc;
+    } else {
+      maps.res[i] = maps.out[i];
+    }
+    flops += 2.0 * c.M * c.N * c.K;
+    bytes += 2.0 * (static_cast<double>(c.M) * c.K + static_cast<double>(c.N) * c.K +
+                    static_cast<double>(c.M) * c.N * (c.epi.residual ? 2 : 1));
+  }
+  for (int i = n; i < kChainMaxPhases; ++i) {
+    maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; maps.out[i] = maps.out[0]; maps.res[i] = maps.res[0];
+    cp.ph[i].tile_begin = tiles;
+  }
+  cp.total_tiles = tiles;
+  const int max_workers = num_sms() / 2;
+  const int workers = tiles < max_workers ? tiles : max_workers;
+  LaunchCfg lc(dim3(static_cast<unsigned>(workers * 2)), dim3(128 + EW * 32), L::kTotal, stream, 2);
+  cudaError_t e;
+  {
+    ProfScope ps(stream, kProfGemm, flops, bytes);
+    if (dtype == kBF16) {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(gemm_chain_kernel<__nv_bfloat16, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal); attr = true; }
+      e = cudaLaunchKernelEx(&lc.cfg, gemm_chain_kernel<__nv_bfloat16, EW>, maps, cp);
+    } else {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(gemm_chain_kernel<__half, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal); attr = true; }
+      e = cudaLaunchKernelEx(&lc.cfg, gemm_chain_kernel<__half, EW>, maps, cp);
+    }
+  }
+  count_launch();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("gemm_chain launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
 }
 
 int gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out,

@@ -152,6 +152,10 @@ struct sf_ctx {
   void *head_kv_w = nullptr, *head_out_w = nullptr, *head_fc1_w = nullptr, *head_fc2_w = nullptr;
   float *head_kv_b = nullptr, *head_out_b = nullptr, *head_fc1_b = nullptr, *head_fc2_b = nullptr;
   float *head_q = nullptr, *head_ln_g = nullptr, *head_ln_b = nullptr;
+  // GEMM-chain dependency counters live in the caller's workspace: zeroed when first seen (the
+  // chain kernels leave them zero)
+  void* chain_ctr_seen = nullptr;
+  size_t chain_ctr_bytes = 0;
 };
 
 // One captured streaming step (sf_forward_stream under a CUDA graph): fixed shapes and buffers, the
@@ -187,6 +191,7 @@ namespace {
 
 struct WsPlan {
   void *qkv, *ctx, *tmp, *mlp;
+  void* chain_ctr = nullptr;   // dependency counters of the GEMM chains (zero between launches)
   // partial row statistics (sum, sumsq) feeding the folded LayerNorms: [0] after the temporal
   // branch, [1] after the spatial branch, [2] at the layer boundary (after the MLP / the embedding)
   float2* stats[3];
@@ -200,7 +205,8 @@ size_t layer_ws_bytes(const sf_ctx* c, long M) {
   const size_t es = 2;
   const size_t D = c->D, I = c->I;
   // qkv[M,3D] ctx[M,D] tmp[M,D] mlp[M,I] stats[3]  (+256 B alignment each)
-  return static_cast<size_t>(M) * (3 * D + D + D + I) * es + 3 * stats_bytes(c, M) + 7 * 256;
+  return static_cast<size_t>(M) * (3 * D + D + D + I) * es + 3 * stats_bytes(c, M) + gemm_chain_counter_bytes(static_cast<int>(M)) +
+         8 * 256;
 }
 
 int carve_layer_ws(const sf_ctx* c, long M, Bump& b, WsPlan& p) {
@@ -210,6 +216,7 @@ int carve_layer_ws(const sf_ctx* c, long M, Bump& b, WsPlan& p) {
   p.tmp = b.take(M * D * es);
   p.mlp = b.take(M * I * es);
   for (int i = 0; i < 3; ++i) p.stats[i] = static_cast<float2*>(b.take(stats_bytes(c, M)));
+  p.chain_ctr = b.take(gemm_chain_counter_bytes(static_cast<int>(M)));
   if (b.overflow) {
     set_error("workspace too small: need at least %zu bytes, have %zu", b.off, b.size);
     return SF_ERR_WORKSPACE;
@@ -230,6 +237,42 @@ GemmEpilogue epi_ln(const float* bias, const float* colsum, const float2* stats,
   return e;
 }
 
+// Runs dependent GEMMs over the same rows: as one persistent chain launch when the geometry allows
+// it (CTA-pair tiles for every call), else one launch per call.  Row statistics handed from call
+// i-1 to call i (stats_out -> ln_stats) use the partial count of whichever path runs.
+int run_gemms(sf_ctx* c, cudaStream_t st, GemmCall* calls, int n, const WsPlan& w, int* last_stats_parts = nullptr) {
+  const int dt = c->cfg.dtype;
+  const bool chain = n >= 2 && w.chain_ctr && gemm_chain_supported(dt, calls, n);
+  if (last_stats_parts)   // partial count of the row statistics the LAST call leaves in its stats_out
+    *last_stats_parts = chain ? gemm_chain_stats_parts(calls, n, calls[n - 1].N) : gemm_stats_parts(calls[n - 1].M, calls[n - 1].N);
+  for (int i = 1; i < n; ++i) {
+    if (calls[i].epi.ln_stats && calls[i].epi.ln_stats == calls[i - 1].epi.stats_out)
+      calls[i].epi.ln_parts = chain ? gemm_chain_stats_parts(calls, n, calls[i - 1].N) : gemm_stats_parts(calls[i - 1].M, calls[i - 1].N);
+  }
+  if (chain) {
+    const size_t bytes = gemm_chain_counter_bytes(calls[0].M);
+    if (c->chain_ctr_seen != w.chain_ctr || c->chain_ctr_bytes != bytes) {
+      SF_CUDA(cudaMemsetAsync(w.chain_ctr, 0, bytes, st));
+      c->chain_ctr_seen = w.chain_ctr;
+      c->chain_ctr_bytes = bytes;
+    }
+    return gemm_chain(st, dt, calls, n, w.chain_ctr);
+  }
+  for (int i = 0; i < n; ++i) {
+    const GemmCall& g = calls[i];
+    SF_CHECK(gemm(st, dt, g.A, g.lda, g.W, g.ldw, g.out, g.ldo, g.M, g.N, g.K, g.epi));
+  }
+  return 0;
+}
+
+GemmCall make_call(const void* A, int lda, const void* W, int ldw, void* out, int ldo, long M, int N, int K,
+                   const GemmEpilogue& e) {
+  GemmCall g;
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.out = out; g.ldo = ldo;
+  g.M = static_cast<int>(M); g.N = N; g.K = K; g.epi = e;
+  return g;
+}
+
 // One divided space-time block.  Rows stay in the residual stream's (b,n,t) order throughout: the
 // temporal branch sees its T frames of a site as consecutive rows, the spatial attention reads the
 // S tokens of a frame in place with a row stride of T (no permute copies, reference :962-991).
@@ -237,21 +280,28 @@ GemmEpilogue epi_ln(const float* bias, const float* colsum, const float2* stats,
 // statistics they need are by-products of the epilogues that wrote the rows:
 //   st_in (x_in) -> temporal QKV ; w.stats[0] (after temporal) -> spatial QKV ;
 //   w.stats[1] (after spatial) -> fc1 ; st_out (after the MLP) -> the next layer.
+// GEMMs that follow each other without an attention kernel in between run as chains:
+//   [temporal out-proj(.temporal_dense) + gated residual -> spatial QKV]
+//   [spatial out-proj + residual -> fc1 + GELU -> fc2 + residual -> the NEXT layer's temporal QKV]
+// qkv_ready: this layer's temporal QKV was produced by the previous layer's chain;
+// next: the following layer (its temporal QKV is appended to this layer's second chain), or null.
 int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, int B, int T, int S,
               sf_kv* kv, float* probs, const WsPlan& w, const float2* st_in, int parts_in, float2* st_out,
-              const int* seen_dev = nullptr) {
+              const int* seen_dev = nullptr, bool qkv_ready = false, const LayerW* next = nullptr,
+              bool* next_qkv_done = nullptr, int* st_out_parts = nullptr) {
   const LayerW& lw = c->layers[l];
   const int D = c->D, I = c->I, H = c->H, dt = c->cfg.dtype;
   const long M = static_cast<long>(B) * S * T;
   const float eps = c->cfg.layer_norm_eps;
   const float scale = 0.125f;  // head_dim**-0.5, head_dim == 64 (…siglip.py:512, 628)
-  const int parts_d = gemm_stats_parts(static_cast<int>(M), D);
+  if (next_qkv_done) *next_qkv_done = false;
 
   // ---- temporal branch (…siglip.py:937-958): rows (b,n,t), T innermost => sites are contiguous
   {
   PhaseScope phase(st, kPhaseAttnBlock);   // the space-time attention block incl. its projections
-  SF_CHECK(gemm(st, dt, x_in, D, lw.t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
-                epi_ln(lw.t_qkv_b, lw.t_qkv_cs, st_in, parts_in, eps)));
+  if (!qkv_ready)
+    SF_CHECK(gemm(st, dt, x_in, D, lw.t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
+                  epi_ln(lw.t_qkv_b, lw.t_qkv_cs, st_in, parts_in, eps)));
   if (kv) {
     SF_CHECK(kv_append(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, B * S, H, T, kv->seen, seen_dev));
     SF_CHECK(temporal_attention(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, w.ctx, D, B * S, H, T,
@@ -261,43 +311,66 @@ int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, 
                                 c->cfg.causal_temporal, scale));
   }
   {
+    // [temporal out-proj (. temporal_dense) + gated residual -> spatial QKV (…siglip.py:954-958, 960-974)]
+    GemmCall calls[3];
+    int n = 0;
     GemmEpilogue e;
     e.residual = x_in; e.ldr = D; e.gate = lw.gate;
     e.stats_out = w.stats[0];
     if (c->cfg.fold_temporal_proj) {
       e.bias = lw.t_fold_b;
-      SF_CHECK(gemm(st, dt, w.ctx, D, lw.t_fold_w, D, x_out, D, M, D, D, e));
+      calls[n++] = make_call(w.ctx, D, lw.t_fold_w, D, x_out, D, M, D, D, e);
     } else {
-      SF_CHECK(gemm(st, dt, w.ctx, D, lw.t_out_w, D, w.tmp, D, M, D, D, epi_bias(lw.t_out_b)));
+      calls[n++] = make_call(w.ctx, D, lw.t_out_w, D, w.tmp, D, M, D, D, epi_bias(lw.t_out_b));
       e.bias = lw.t_dense_b;
-      SF_CHECK(gemm(st, dt, w.tmp, D, lw.t_dense_w, D, x_out, D, M, D, D, e));
+      calls[n++] = make_call(w.tmp, D, lw.t_dense_w, D, x_out, D, M, D, D, e);
     }
+    calls[n++] = make_call(x_out, D, lw.s_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
+                           epi_ln(lw.s_qkv_b, lw.s_qkv_cs, w.stats[0], 0, eps));
+    SF_CHECK(run_gemms(c, st, calls, n, w));
   }
   // ---- spatial branch (…siglip.py:960-996)
-  SF_CHECK(gemm(st, dt, x_out, D, lw.s_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
-                epi_ln(lw.s_qkv_b, lw.s_qkv_cs, w.stats[0], parts_d, eps)));
   SF_CHECK(spatial_attention(st, dt, w.qkv, 3 * D, w.ctx, D, B * T, H, S, T, scale, probs));
+  }
+  // ---- [spatial out-proj + residual -> MLP (…siglip.py:993-1000) -> next layer's temporal QKV]
+  GemmCall calls[4];
+  int n = 0;
+  int s_out_parts = 0;
   {
     GemmEpilogue e = epi_bias(lw.s_out_b);
     e.residual = x_out; e.ldr = D;
     e.stats_out = w.stats[1];
-    SF_CHECK(gemm(st, dt, w.ctx, D, lw.s_out_w, D, x_out, D, M, D, D, e));
+    calls[n++] = make_call(w.ctx, D, lw.s_out_w, D, x_out, D, M, D, D, e);
   }
+  if (phase_prof_enabled()) {
+    // per-phase timing: the out-projection belongs to the attention block, so it runs on its own
+    // inside that phase instead of heading the MLP chain (a slightly less fused schedule than production)
+    PhaseScope attn_tail(st, kPhaseAttnBlock);
+    SF_CHECK(run_gemms(c, st, calls, 1, w, &s_out_parts));
+    n = 0;
   }
-  // ---- MLP (…siglip.py:997-1000)
   PhaseScope phase(st, kPhaseMlp);
   {
-    GemmEpilogue e = epi_ln(lw.fc1_b, lw.fc1_cs, w.stats[1], parts_d, eps);
+    GemmEpilogue e = epi_ln(lw.fc1_b, lw.fc1_cs, w.stats[1], s_out_parts, eps);
     e.act = c->cfg.hidden_act;
-    SF_CHECK(gemm(st, dt, x_out, D, lw.fc1_w, D, w.mlp, I, M, I, D, e));
+    calls[n++] = make_call(x_out, D, lw.fc1_w, D, w.mlp, I, M, I, D, e);
   }
   {
     GemmEpilogue e = epi_bias(lw.fc2_b);
     e.residual = x_out; e.ldr = D;
     e.stats_out = st_out;
-    SF_CHECK(gemm(st, dt, w.mlp, I, lw.fc2_w, I, x_out, D, M, D, I, e));
+    calls[n++] = make_call(w.mlp, I, lw.fc2_w, I, x_out, D, M, D, I, e);
   }
-  return 0;
+  if (next && st_out) {
+    calls[n] = make_call(x_out, D, next->t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
+                         epi_ln(next->t_qkv_b, next->t_qkv_cs, st_out, 0, eps));
+    if (gemm_chain_supported(dt, calls, n + 1)) {
+      ++n;
+      if (next_qkv_done) *next_qkv_done = true;
+      return run_gemms(c, st, calls, n, w);     // (st_out is consumed inside the chain)
+    }
+  }
+  return run_gemms(c, st, calls, n, w, st_out_parts);
 }
 
 int run_embed(sf_ctx* c, cudaStream_t st, const void* pixels, int pix_dtype, int B, int T, int Hh, int Ww,
@@ -411,11 +484,18 @@ int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int 
     SF_CHECK(run_embed(c, st, pixels, pix_dtype, B, T, Hh, Ww, time_off, time_total, cur, w.mlp, w.stats[2],
                        dev_seen ? kv->d_seen : nullptr, dev_seen ? kv->horizon : 0));
   }
-  const int parts_d = gemm_stats_parts(static_cast<int>(M), D);
+  int parts_d = gemm_stats_parts(static_cast<int>(M), D);   // partials left by the embedding GEMM
+  bool qkv_ready = false;
   for (int l = 0; l < c->L; ++l) {
     void* nxt = hidden_states ? hidden_states[l + 1] : cur;
+    // the phase profiler times the attention block of each layer on its own: keep the next layer's
+    // QKV out of this layer's MLP chain then
+    const LayerW* next = (l + 1 < c->L && !phase_prof_enabled()) ? &c->layers[l + 1] : nullptr;
+    bool next_done = false;
     SF_CHECK(run_layer(c, st, l, cur, nxt, B, T, S, kv, attentions ? static_cast<float*>(attentions[l]) : nullptr, w,
-                       w.stats[2], parts_d, w.stats[2], dev_seen ? kv->d_seen : nullptr));
+                       w.stats[2], parts_d, w.stats[2], dev_seen ? kv->d_seen : nullptr, qkv_ready, next, &next_done,
+                       &parts_d));
+    qkv_ready = next_done;
     cur = nxt;
   }
   if (kv && !dev_seen) {
@@ -671,6 +751,11 @@ extern "C" {
 const char* sf_last_error(void) { return last_error(); }
 const char* sf_version(void) { return "streamformer_b200 0.1 (sm_100a)"; }
 uint64_t sf_launch_count(void) { return launch_count(); }
+int sf_set_option(const char* name, int value) {
+  if (name && strcmp(name, "gemm_chain") == 0) { set_gemm_chain(value); return 0; }
+  set_error("sf_set_option: unknown option '%s'", name ? name : "(null)");
+  return SF_ERR_INVALID;
+}
 int sf_profile(int mode) { prof_set_mode(mode); return 0; }
 int sf_profile_collect_phases(double* ms, long long* count, int n_phases) { return phase_collect(ms, count, n_phases); }
 int sf_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int n_classes) {

@@ -57,6 +57,25 @@ struct GemmEpilogue {
 int gemm(cudaStream_t stream, int dtype, const void* A, int lda, const void* W, int ldw, void* out,
          int ldo, int M, int N, int K, const GemmEpilogue& epi);
 
+// Several dependent GEMMs over the same M rows as ONE persistent launch (see gemm_tcgen05.cu,
+// "GEMM chains"): call i may read the output rows and the row statistics (stats_out -> ln_stats,
+// gemm_chain_stats_parts(calls, n, N) partials per row) of call i-1 and, as residual, rows written by any
+// earlier call of the chain.  `counters` is gemm_chain_counter_bytes(M) of device memory that must
+// be zero before the first launch; the kernel leaves it zero again (no host-side state, so a
+// captured launch can be replayed).
+struct GemmCall {
+  const void* A; int lda;
+  const void* W; int ldw;
+  void* out; int ldo;
+  int M, N, K;
+  GemmEpilogue epi;
+};
+bool gemm_chain_supported(int dtype, const GemmCall* calls, int n);
+void set_gemm_chain(int on);   // -1: environment default (SF_GEMM_CHAIN, off), 0 / 1: force
+int gemm_chain_stats_parts(const GemmCall* calls, int n, int N);
+size_t gemm_chain_counter_bytes(int M);
+int gemm_chain(cudaStream_t stream, int dtype, const GemmCall* calls, int n, void* counters);
+
 // Number of column groups (partials per row) gemm() writes to GemmEpilogue::stats_out for an M x N output.
 int gemm_stats_parts(int M, int N);
 // Upper bound of gemm_stats_parts over all tile shapes (columns per partial >= 64).

@@ -92,6 +92,37 @@ def test_matches_oracle_full_tensors(fold):
     check("last_hidden_state", out.last_hidden_state, ref["last_hidden_state"], t["lhs"], t["cos"])
 
 
+@pytest.mark.parametrize("name", ["stress_l2_lora", "long_t128_l1"])
+def test_gemm_chain_schedule_matches_golden(name):
+    """The opt-in chained schedule (several dependent GEMMs as one persistent launch with in-kernel row
+    dependencies) must give the same answer: M = 6272 exercises the short-chain case where a tile's
+    producer sits exactly one round earlier on the same worker, M = 25088 the bench geometry."""
+    from streamformer_b200 import _native as N
+    case, z = load_golden(name)
+    cfg, w, px = case_inputs(case)
+    model = build_model(cfg, w)
+    pxc = torch.from_numpy(px).cuda()
+    with torch.no_grad():
+        base = model(pxc)
+        n0 = N.launch_count()
+        model(pxc)
+        per_gemm = N.launch_count() - n0
+        N.set_option("gemm_chain", 1)
+        try:
+            n0 = N.launch_count()
+            out = model(pxc)
+            torch.cuda.synchronize()
+            chained = N.launch_count() - n0
+        finally:
+            N.set_option("gemm_chain", -1)
+    assert chained < per_gemm, "the chained schedule did not engage"
+    t = TOL[torch.bfloat16]
+    check(name + " chain last_hidden_state", sub(out.last_hidden_state.float().cpu().numpy()), z["last_hidden_state_sub"], t["lhs"], t["cos"])
+    check(name + " chain pooler_output", out.pooler_output, z["pooler_output"], t["pool"], t["cos"])
+    # and against the default schedule (different epilogue warp counts / partial-sum order: tolerance, not bitwise)
+    check(name + " chain vs default", out.last_hidden_state, base.last_hidden_state.float().cpu().numpy(), t["lhs"], t["cos"])
+
+
 def test_fp32_parameters_compute_in_bf16_and_return_fp32():
     cfg = O.OracleConfig(num_hidden_layers=1)
     w = O.make_weights(cfg, seed=22, style="stress")
