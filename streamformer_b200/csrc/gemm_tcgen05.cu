@@ -486,38 +486,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ln) c4[v] = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + col));
         }
       }
-      constexpr int kMaxParts = 6;                      // partials held in registers per row
-      float2 t[kBM / 32][kMaxParts];
+      // row statistics: up to 12 partials per row (64-column producers) held in registers, two row
+      // groups per round trip
+      constexpr int kMaxParts = 12;
       float s1x[kBM / 32], s2x[kBM / 32];
       if constexpr (kLnCapable) {
         if (ln) {
 #pragma unroll
-          for (int rr = 0; rr < kBM / 32; ++rr) {
-            const int m = m0 + rr * 32 + lane;
+          for (int half = 0; half < kBM / 64; ++half) {
+            float2 t[2][kMaxParts];
 #pragma unroll
-            for (int q = 0; q < kMaxParts; ++q) {
-              t[rr][q] = make_float2(0.f, 0.f);
-              if (q < e.ln_parts && m < p.M) t[rr][q] = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
-            }
-          }
+            for (int rr = 0; rr < 2; ++rr) {
+              const int m = m0 + (half * 2 + rr) * 32 + lane;
 #pragma unroll
-          for (int rr = 0; rr < kBM / 32; ++rr) {
-            const int m = m0 + rr * 32 + lane;
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int q = 0; q < kMaxParts; ++q) {
-              s1 += t[rr][q].x;
-              s2 += t[rr][q].y;
-            }
-            for (int q = kMaxParts; q < e.ln_parts; ++q) {   // more partials than registers (small-N producers)
-              if (m < p.M) {
-                const float2 u = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
-                s1 += u.x;
-                s2 += u.y;
+              for (int q = 0; q < kMaxParts; ++q) {
+                t[rr][q] = make_float2(0.f, 0.f);
+                if (q < e.ln_parts && m < p.M) t[rr][q] = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
               }
             }
-            s1x[rr] = s1;
-            s2x[rr] = s2;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int m = m0 + (half * 2 + rr) * 32 + lane;
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int q = 0; q < kMaxParts; ++q) {
+                s1 += t[rr][q].x;
+                s2 += t[rr][q].y;
+              }
+              for (int q = kMaxParts; q < e.ln_parts; ++q) {   // (never with the shipped tile shapes)
+                if (m < p.M) {
+                  const float2 u = __ldg(e.ln_stats + static_cast<long>(q) * p.M + m);
+                  s1 += u.x;
+                  s2 += u.y;
+                }
+              }
+              s1x[half * 2 + rr] = s1;
+              s2x[half * 2 + rr] = s2;
+            }
           }
         }
       }
@@ -1743,8 +1748,8 @@ int launch_chain(cudaStream_t stream, int dtype, const GemmCall* calls, int n, v
     P.tile_begin = tiles;
     tiles += cp.m_tiles * P.n_tiles;
     P.mode = c.epi.residual ? kEpiResidual : (c.epi.act != kActNone ? kEpiAct : kEpiBias);
-    P.signal = i + 1 < n ? 1 : 0;
     P.expected = static_cast<uint32_t>(P.n_tiles) * 2u * EW;
+    P.signal = i + 1 < n ? 1 : 0;
     P.out = c.out; P.ldo = c.ldo;
     P.epi = c.epi;
     int rc = make_operand_map(&maps.a[i], dtype, c.A, c.M, c.K, c.lda, kBM);
