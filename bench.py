@@ -26,9 +26,9 @@ sys.path.insert(0, ROOT)
 METRIC = "encoder frames/sec at [B,16,3,224,224]"
 UNIT = "frames/s"
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one cfg2 step
-# (per layer: 107.9 + 84.2 + 108.0 + 82.3 + 147.5 + 249.6 MB from profiles/r1_ncu_layer.md, x 12 layers;
+# (per layer: 108.3 + 85.8 + 108.9 + 82.8 + 147.4 + 224.3 MB from profiles/r1_ncu_layer.md, x 12 layers;
 # embed and head GEMMs estimated at their algorithmic bytes, 0.25 GB)
-NCU_GEMM_TRAFFIC_BYTES = 12 * (107.9 + 84.2 + 108.0 + 82.3 + 147.5 + 249.6) * 1e6 + 0.25e9
+NCU_GEMM_TRAFFIC_BYTES = 12 * (108.3 + 85.8 + 108.9 + 82.8 + 147.4 + 224.3) * 1e6 + 0.25e9
 
 
 def parse_args():
@@ -351,7 +351,8 @@ def run_ours(args):
             "mlp_ms_per_layer": phases["mlp"]["ms"] / (args.layers * PK),
             "embed_ms": phases["embed"]["ms"] / max(phases["embed"]["count"], 1),
             "head_ms": phases["head"]["ms"] / max(phases["head"]["count"], 1),
-            "how": "CUDA events around the block of every layer (sf_profile mode 2), kernels back to back with PDL",
+            "how": "CUDA events around the attention block of every layer (sf_profile mode 2: temporal QKV .. spatial "
+                   "attention, then the spatial out-projection), kernels back to back with PDL",
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
