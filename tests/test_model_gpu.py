@@ -123,6 +123,42 @@ def test_gemm_chain_schedule_matches_golden(name):
     check(name + " chain vs default", out.last_hidden_state, base.last_hidden_state.float().cpu().numpy(), t["lhs"], t["cos"])
 
 
+def test_full_size_bench_config_properties():
+    """BASELINE.json configs[1] at full size (B=8, T=16, 224x224, 12 layers, bf16 — the bench workload):
+    the reference's own full-depth golden clip placed inside the batch must come out within tolerance,
+    and the size-independent invariants must hold exactly: a clip's result does not depend on its
+    batch slot or on the other clips of the launch (different tile / CTA assignment), perturbing the
+    last frame leaves every earlier frame bit-identical, and the run is deterministic."""
+    case, z = load_golden("full_l12")
+    cfg, w, px = case_inputs(case)
+    model = build_model(cfg, w)
+    g = torch.Generator().manual_seed(99)
+    batch = torch.randn(8, 16, 3, 224, 224, generator=g)
+    batch[3] = torch.from_numpy(px)[0]
+    batch[6] = torch.from_numpy(px)[0]
+    batch = batch.cuda()
+    with torch.no_grad():
+        out = model(batch)
+        again = model(batch)
+        single = model(batch[3:4])
+        pert = batch.clone()
+        pert[:, 15] += 0.5
+        out_p = model(pert)
+    t = TOL[torch.bfloat16]
+    check("golden clip inside the batch: pooler_output", out.pooler_output[3:4], z["pooler_output"], t["pool"], t["cos"])
+    check("golden clip inside the batch: last_hidden_state", sub(out.last_hidden_state[3:4].float().cpu().numpy()),
+          z["last_hidden_state_sub"], t["lhs"], t["cos"])
+    assert torch.equal(out.last_hidden_state, again.last_hidden_state) and torch.equal(out.pooler_output, again.pooler_output)
+    assert torch.equal(out.last_hidden_state[3], out.last_hidden_state[6]), "same clip, different batch slot"
+    # alone (M = 3136) the GEMMs pick other tile shapes, so the LayerNorm statistics are summed in a
+    # different order: equal within the dtype tolerance, not bitwise
+    check("clip alone vs inside the batch", single.last_hidden_state[0], out.last_hidden_state[3].float().cpu().numpy(), t["lhs"], t["cos"])
+    check("clip alone vs inside the batch (pooled)", single.pooler_output[0], out.pooler_output[3].float().cpu().numpy(), t["pool"], t["cos"])
+    assert torch.equal(out.last_hidden_state[:, :15], out_p.last_hidden_state[:, :15]), "causality at full size"
+    assert torch.equal(out.pooler_output[:, :15], out_p.pooler_output[:, :15])
+    assert not torch.equal(out.last_hidden_state[:, 15], out_p.last_hidden_state[:, 15])
+
+
 def test_fp32_parameters_compute_in_bf16_and_return_fp32():
     cfg = O.OracleConfig(num_hidden_layers=1)
     w = O.make_weights(cfg, seed=22, style="stress")
