@@ -198,6 +198,12 @@ int sf_op_rowstats(void* stream, int dtype, const void* x, int ldx, int M, int D
 int sf_op_gemm_stats_parts(int M, int N);
 int sf_op_pool_attention(void* stream, int dtype, const void* kv, int ld_kv, const float* q, void* out,
                          int ld_out, int frames, int heads, int S);
+/* The pooling attention of the SigLIP head with its key / value projections collapsed into it (the
+ * query is one learned probe, …siglip.py:1141-1148): tokens [frames*S, D] -> out [frames, D] =
+ * concat_h(W_v,h s_h + b_v,h), s_h = softmax_n(x_n . u_h)-weighted token sum.  u [heads, D] fp32 =
+ * W_k,h^T q_h with q the scaled probe query, wv [D, D] (activation dtype, nn.Linear layout), bv [D] fp32. */
+int sf_op_pool_probe(void* stream, int dtype, const void* tokens, int ld, const float* u, const void* wv,
+                     const float* bv, void* out, int ld_out, int frames, int heads, int S);
 
 #ifdef __cplusplus
 }

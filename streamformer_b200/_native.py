@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_kv_graph_launches", "sf_forward_stream",
     "sf_embed_forward", "sf_layer_forward", "sf_final_norm", "sf_head_forward",
     "sf_op_gemm", "sf_op_layernorm", "sf_op_im2col", "sf_op_temporal_attention", "sf_op_kv_append",
-    "sf_op_spatial_attention", "sf_op_pool_attention", "sf_op_rowstats", "sf_op_gemm_stats_parts",
+    "sf_op_spatial_attention", "sf_op_pool_attention", "sf_op_pool_probe", "sf_op_rowstats", "sf_op_gemm_stats_parts",
 ]
 
 
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     lib.sf_op_rowstats.argtypes = [vp, i, vp, i, i, i, vp]
     lib.sf_op_gemm_stats_parts.argtypes = [i, i]
     lib.sf_op_pool_attention.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i]
+    lib.sf_op_pool_probe.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, i, i, i]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("sf_last_error", "sf_version", "sf_launch_count", "sf_kv_graph_launches"):

@@ -456,6 +456,181 @@ pool_attn_kernel(const T* __restrict__ kv, long ld, const float* __restrict__ q,
   *reinterpret_cast<uint32_t*>(out + frame * out_ld + h * kHd + 2 * lane) = Pack2<T>::pack(o0 * inv, o1 * inv);
 }
 
+// ------------------------------------------------------------------------------- pooling probe, collapsed
+// The SigLIP pooling head attends with ONE learned probe (reference :1141-1148), so its key and value
+// projections never have to be materialised: with q_h the (scaled) probe query of head h,
+//   score_h(n) = q_h . (W_k,h x_n + b_k,h) = x_n . u_h + const,   u_h = W_k,h^T q_h   (const cancels in softmax)
+//   out_h      = sum_n p_h(n) (W_v,h x_n + b_v,h) = W_v,h (sum_n p_h(n) x_n) + b_v,h
+// i.e. 12 dot products per token, a probability-weighted token sum per head and one 64 x D mat-vec
+// per head and frame — instead of a [tokens, D] x [D, 2D] GEMM (59 GFLOP and 77 MB at cfg2) plus an
+// attention pass over its output.  One CTA per frame, one warp per head; tokens stream through shared
+// memory in chunks twice (scores, then the weighted sum; the second pass hits L2).
+constexpr int kProbeChunk = 16;     // tokens per shared-memory chunk (staged as fp32)
+constexpr int kProbeMaxD = 1024;
+template <typename T>
+__global__ void __launch_bounds__(512)
+pool_probe_kernel(const T* __restrict__ x, long ld, const float* __restrict__ u, const T* __restrict__ wv,
+                  const float* __restrict__ bv, T* __restrict__ out, long out_ld, int heads, int S) {
+  extern __shared__ __align__(16) uint8_t psm[];
+  const int D = heads * kHd;
+  const int Sp = (S + 3) & ~3;
+  float* sx = reinterpret_cast<float*>(psm);                                       // [2][kProbeChunk][D] fp32
+  float* sc = sx + 2 * kProbeChunk * D;                                            // [heads][Sp]
+  float* sv = sc + heads * Sp;                                                     // [heads][D] pooled tokens
+  griddep_wait();
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp == head
+  const long frame = blockIdx.x;
+  const T* xf = x + frame * S * ld;
+  const int groups = D / 128;                                   // float4 per lane and row (6 for D = 768)
+  constexpr int kMaxGroups = kProbeMaxD / 128;
+  // this lane's slice of u_h: elements g*128 + lane*4 .. +3
+  float4 ur[kMaxGroups];
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g)
+    ur[g] = g < groups ? __ldg(reinterpret_cast<const float4*>(u + warp * D + g * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // staging: every thread moves `per_thread` 8-element pieces of a chunk (global 16-bit -> shared fp32);
+  // the next chunk's pieces are fetched into registers before the current one is consumed
+  const int chunks = (S + kProbeChunk - 1) / kProbeChunk;
+  const int pieces_per_chunk = kProbeChunk * D / 8;
+  constexpr int kMaxPer = 8;
+  const int per_thread = (pieces_per_chunk + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);   // 4 at D=768, 384 threads
+  uint4 stage[kMaxPer];
+  auto fetch = [&](int c) {
+    const int n0 = c * kProbeChunk;
+#pragma unroll
+    for (int q = 0; q < kMaxPer; ++q) {
+      stage[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (q < per_thread) {
+        const int i = q * blockDim.x + threadIdx.x;
+        const int r = i / (D / 8), piece = i % (D / 8);
+        if (i < pieces_per_chunk && n0 + r < S) stage[q] = *reinterpret_cast<const uint4*>(xf + static_cast<long>(n0 + r) * ld + piece * 8);
+      }
+    }
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < kMaxPer; ++q) {
+      if (q < per_thread) {
+        const int i = q * blockDim.x + threadIdx.x;
+        if (i < pieces_per_chunk) {
+          const float2 a = Pack2<T>::unpack(stage[q].x), b = Pack2<T>::unpack(stage[q].y);
+          const float2 c2 = Pack2<T>::unpack(stage[q].z), d = Pack2<T>::unpack(stage[q].w);
+          float4* dst = reinterpret_cast<float4*>(sx + buf * kProbeChunk * D + i * 8);
+          dst[0] = make_float4(a.x, a.y, b.x, b.y);
+          dst[1] = make_float4(c2.x, c2.y, d.x, d.y);
+        }
+      }
+    }
+  };
+
+  // ---- pass 1: scores of this head for every token
+  fetch(0);
+  for (int c = 0; c < chunks; ++c) {
+    const int buf = c & 1;
+    commit(buf);
+    if (c + 1 < chunks) fetch(c + 1);
+    __syncthreads();                       // chunk c staged (buffer buf was last read two chunks ago)
+    const float* xb = sx + buf * kProbeChunk * D;
+    float part[kProbeChunk];
+#pragma unroll
+    for (int r = 0; r < kProbeChunk; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        if (g < groups) {
+          const float4 xv = *reinterpret_cast<const float4*>(xb + r * D + g * 128 + lane * 4);
+          acc = fmaf(xv.x, ur[g].x, fmaf(xv.y, ur[g].y, fmaf(xv.z, ur[g].z, fmaf(xv.w, ur[g].w, acc))));
+        }
+      }
+      part[r] = acc;
+    }
+    // transpose-reduce 16 partial sums over the warp: lane l ends with the total of token (l & 15)
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {      // 16 -> 8 -> 4 -> 2 -> 1 values per lane
+      const int bit = w;                    // lanes with (lane & bit) keep the upper half
+#pragma unroll
+      for (int i = 0; i < w; ++i) {
+        const float keep = (lane & bit) ? part[i + w] : part[i];
+        const float send = (lane & bit) ? part[i] : part[i + w];
+        part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    }
+    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 16);
+    // after the butterfly lane l holds token index with bits (l&8 -> +8, l&4 -> +4, l&2 -> +2, l&1 -> +1)
+    if (lane < 16) {
+      const int n = c * kProbeChunk + lane;
+      if (n < S) sc[warp * Sp + n] = part[0];
+    }
+    // (no barrier here: the next iteration writes the OTHER buffer, and its __syncthreads orders
+    // this chunk's reads before the write two iterations ahead)
+  }
+  __syncwarp();
+  // ---- softmax over the frame's tokens (this warp's head)
+  float mx = -INFINITY;
+  for (int n = lane; n < S; n += 32) mx = fmaxf(mx, sc[warp * Sp + n]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int n = lane; n < S; n += 32) {
+    const float e = __expf(sc[warp * Sp + n] - mx);
+    sc[warp * Sp + n] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  __syncthreads();                         // every warp is done with pass 1's buffers
+  // ---- pass 2: s = sum_n p(n) x_n; lane owns elements g*128 + lane*4 .. +3
+  float4 acc[kMaxGroups];
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fetch(0);
+  for (int c = 0; c < chunks; ++c) {
+    const int buf = c & 1;
+    commit(buf);
+    if (c + 1 < chunks) fetch(c + 1);
+    __syncthreads();
+    const float* xb = sx + buf * kProbeChunk * D;
+    const int rows = S - c * kProbeChunk < kProbeChunk ? S - c * kProbeChunk : kProbeChunk;
+    for (int r = 0; r < rows; ++r) {
+      const float p = sc[warp * Sp + c * kProbeChunk + r];
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        if (g < groups) {
+          const float4 xv = *reinterpret_cast<const float4*>(xb + r * D + g * 128 + lane * 4);
+          acc[g].x = fmaf(p, xv.x, acc[g].x); acc[g].y = fmaf(p, xv.y, acc[g].y);
+          acc[g].z = fmaf(p, xv.z, acc[g].z); acc[g].w = fmaf(p, xv.w, acc[g].w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) {
+    if (g < groups)
+      *reinterpret_cast<float4*>(sv + warp * D + g * 128 + lane * 4) = make_float4(acc[g].x * inv, acc[g].y * inv, acc[g].z * inv, acc[g].w * inv);
+  }
+  __syncwarp();
+  // ---- value projection of the pooled token: lane computes outputs d = lane and d = lane + 32 of this head
+  const float* sh = sv + warp * D;
+  const T* w0 = wv + static_cast<long>(warp * kHd + lane) * D;
+  const T* w1 = w0 + static_cast<long>(32) * D;
+  float r0 = 0.f, r1 = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < D; k += 8) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(w0 + k));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(w1 + k));
+    const float4 s0 = *reinterpret_cast<const float4*>(sh + k);
+    const float4 s1 = *reinterpret_cast<const float4*>(sh + k + 4);
+    const float2 a0 = Pack2<T>::unpack(a.x), a1 = Pack2<T>::unpack(a.y), a2 = Pack2<T>::unpack(a.z), a3 = Pack2<T>::unpack(a.w);
+    const float2 b0 = Pack2<T>::unpack(b.x), b1 = Pack2<T>::unpack(b.y), b2 = Pack2<T>::unpack(b.z), b3 = Pack2<T>::unpack(b.w);
+    r0 += a0.x * s0.x + a0.y * s0.y + a1.x * s0.z + a1.y * s0.w + a2.x * s1.x + a2.y * s1.y + a3.x * s1.z + a3.y * s1.w;
+    r1 += b0.x * s0.x + b0.y * s0.y + b1.x * s0.z + b1.y * s0.w + b2.x * s1.x + b2.y * s1.y + b3.x * s1.z + b3.y * s1.w;
+  }
+  T* orow = out + frame * out_ld + warp * kHd;
+  orow[lane] = static_cast<T>(r0 + __ldg(bv + warp * kHd + lane));
+  orow[lane + 32] = static_cast<T>(r1 + __ldg(bv + warp * kHd + lane + 32));
+}
+
 int check_launch(const char* what) {
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -559,6 +734,40 @@ int spatial_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_qk
   else cudaLaunchKernelEx(&lp.cfg, spatial_probs_kernel<__half>, reinterpret_cast<const __half*>(qkv),
                           static_cast<long>(ld_qkv), probs, frames, heads, S, T_inner, scale);
   return check_launch("spatial_probs");
+}
+
+int pool_probe(cudaStream_t stream, int dtype, const void* tokens, int ld, const float* u, const void* wv, const float* bv,
+               void* out, int ld_out, int frames, int heads, int S) {
+  if (frames <= 0) return 0;
+  const int D = heads * kHd;
+  if (dtype != kBF16 && dtype != kF16) { set_error("pool_probe: dtype must be bf16/f16"); return -1; }
+  if (heads < 1 || heads > 16 || (D % 128) || D > kProbeMaxD || S < 1 || (ld % 8) ||
+      kProbeChunk * D / 8 > 8 * heads * 32) {
+    set_error("pool_probe: unsupported geometry (heads %d, D %d, S %d)", heads, D, S);
+    return -1;
+  }
+  const size_t smem = static_cast<size_t>(2) * kProbeChunk * D * 4 + static_cast<size_t>(heads) * ((S + 3) & ~3) * 4 +
+                      static_cast<size_t>(heads) * D * 4;
+  if (smem > 227 * 1024) { set_error("pool_probe: S=%d needs %zu bytes of shared memory", S, smem); return -1; }
+  ProfScope ps(stream, kProfPoolAttn, 2.0 * frames * (2.0 * S * heads * D + static_cast<double>(D) * D),
+               2.0 * frames * S * D * 2.0);
+  LaunchCfg lc(dim3(static_cast<unsigned>(frames)), dim3(heads * 32), smem, stream);
+  cudaError_t e;
+  if (dtype == kBF16) {
+    e = cudaFuncSetAttribute(pool_probe_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaLaunchKernelEx(&lc.cfg, pool_probe_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(tokens), static_cast<long>(ld), u,
+                             reinterpret_cast<const __nv_bfloat16*>(wv), bv, reinterpret_cast<__nv_bfloat16*>(out),
+                             static_cast<long>(ld_out), heads, S);
+  } else {
+    e = cudaFuncSetAttribute(pool_probe_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaLaunchKernelEx(&lc.cfg, pool_probe_kernel<__half>, reinterpret_cast<const __half*>(tokens), static_cast<long>(ld), u,
+                             reinterpret_cast<const __half*>(wv), bv, reinterpret_cast<__half*>(out), static_cast<long>(ld_out),
+                             heads, S);
+  }
+  (void)e;
+  return check_launch("pool_probe");
 }
 
 int pool_attention(cudaStream_t stream, int dtype, const void* kv, int ld_kv, const float* q, void* out,

@@ -63,6 +63,15 @@ __global__ void matmul_nn_kernel(float* __restrict__ C, const float* __restrict_
   }
   if (m < M && n < N) C[static_cast<long>(m) * N + n] = acc;
 }
+// u[h][k] = sum_d Wk[h*64 + d][k] * q[h*64 + d]: the pooling probe pushed through the key projection
+__global__ void head_u_kernel(float* __restrict__ u, const float* __restrict__ Wk, const float* __restrict__ q, int H, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * D) return;
+  const int h = idx / D, k = idx % D;
+  float acc = 0.f;
+  for (int d = 0; d < 64; ++d) acc += Wk[static_cast<long>(h * 64 + d) * D + k] * q[h * 64 + d];
+  u[idx] = acc;
+}
 __global__ void matvec_kernel(float* __restrict__ y, const float* __restrict__ W,
                               const float* __restrict__ x, const float* __restrict__ b, int O, int I,
                               float scale) {
@@ -152,6 +161,7 @@ struct sf_ctx {
   void *head_kv_w = nullptr, *head_out_w = nullptr, *head_fc1_w = nullptr, *head_fc2_w = nullptr;
   float *head_kv_b = nullptr, *head_out_b = nullptr, *head_fc1_b = nullptr, *head_fc2_b = nullptr;
   float *head_q = nullptr, *head_ln_g = nullptr, *head_ln_b = nullptr;
+  float* head_u = nullptr;     // [heads, D]: W_k,h^T q_h (the probe pushed through the key projection)
   // GEMM-chain dependency counters live in the caller's workspace: zeroed when first seen (the
   // chain kernels leave them zero)
   void* chain_ctr_seen = nullptr;
@@ -415,9 +425,19 @@ int run_head(sf_ctx* c, cudaStream_t st, const void* tokens, int frames, int S, 
     set_error("workspace too small for the pooling head: need %zu bytes, have %zu", b.off, b.size);
     return SF_ERR_WORKSPACE;
   }
-  // K/V projection of every token (in_proj rows D..3D), probe attention, out_proj (…siglip.py:1146-1148)
-  SF_CHECK(gemm(st, dt, tokens, D, c->head_kv_w, D, kvbuf, 2 * D, M, 2 * D, D, epi_bias(c->head_kv_b)));
-  SF_CHECK(pool_attention(st, dt, kvbuf, 2 * D, c->head_q, pc, D, frames, H, S));
+  // K/V projection of every token (in_proj rows D..3D) + probe attention (…siglip.py:1146-1148), or —
+  // opt-in, SF_HEAD_COLLAPSE=1 — the same attention with the K/V projections collapsed into it
+  // (pool_probe in attention.cu: exact algebra, 59 GFLOP and 77 MB less per cfg2 step, but its CUDA-core
+  // implementation is shared-memory-bandwidth bound and currently SLOWER: 187 vs 87 us; it needs the
+  // mma.sync formulation before it can become the default)
+  static const bool collapse = [] { const char* e = getenv("SF_HEAD_COLLAPSE"); return e && e[0] == '1'; }();
+  if (collapse && H <= 16 && D % 256 == 0 && D <= 1024 && S <= 2048) {
+    SF_CHECK(pool_probe(st, dt, tokens, D, c->head_u, static_cast<const uint8_t*>(c->head_kv_w) + static_cast<size_t>(D) * D * es,
+                        c->head_kv_b + D, pc, D, frames, H, S));
+  } else {
+    SF_CHECK(gemm(st, dt, tokens, D, c->head_kv_w, D, kvbuf, 2 * D, M, 2 * D, D, epi_bias(c->head_kv_b)));
+    SF_CHECK(pool_attention(st, dt, kvbuf, 2 * D, c->head_q, pc, D, frames, H, S));
+  }
   SF_CHECK(gemm(st, dt, pc, D, c->head_out_w, D, r, D, frames, D, D, epi_bias(c->head_out_b)));
   // r + MLP(LN(r)) (…siglip.py:1150-1152)
   SF_CHECK(layernorm(st, dt, r, D, c->head_ln_g, c->head_ln_b, c->cfg.layer_norm_eps, lnr, D, frames, D,
@@ -907,6 +927,14 @@ int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
                                                                         b.scratch[1], static_cast<int>(D),
                                                                         static_cast<int>(D), 0.125f);
       count_launch();
+      // u_h = W_k,h^T q_h (fp32): the collapsed pooling attention scores tokens directly
+      SF_CHECK(cast(st, ipw->dtype, static_cast<const uint8_t*>(ipw->data) + static_cast<size_t>(D) * D * es_in, kF32,
+                    b.scratch[0], D * D));
+      c->head_u = static_cast<float*>(b.arena.take(static_cast<size_t>(c->H) * D * sizeof(float)));
+      if (!c->head_u) { set_error("sf_bind_weights: arena exhausted at head_u"); return SF_ERR_STATE; }
+      head_u_kernel<<<static_cast<unsigned>((c->H * D + 255) / 256), 256, 0, st>>>(c->head_u, b.scratch[0], c->head_q, c->H,
+                                                                                   static_cast<int>(D));
+      count_launch();
     }
     SF_CHECK(b.mat("head.attention.out_proj.weight", D, D, &c->head_out_w));
     SF_CHECK(b.vec("head.attention.out_proj.bias", D, &c->head_out_b));
@@ -1099,6 +1127,10 @@ int sf_op_rowstats(void* stream, int dtype, const void* x, int ldx, int M, int D
   return rowstats(static_cast<cudaStream_t>(stream), dtype, x, ldx, M, D, static_cast<float2*>(stats));
 }
 int sf_op_gemm_stats_parts(int M, int N) { return gemm_stats_parts(M, N); }
+int sf_op_pool_probe(void* stream, int dtype, const void* tokens, int ld, const float* u, const void* wv, const float* bv,
+                     void* out, int ld_out, int frames, int heads, int S) {
+  return pool_probe(static_cast<cudaStream_t>(stream), dtype, tokens, ld, u, wv, bv, out, ld_out, frames, heads, S);
+}
 int sf_op_pool_attention(void* stream, int dtype, const void* kv, int ld_kv, const float* q, void* out, int ld_out,
                          int frames, int heads, int S) {
   return pool_attention(static_cast<cudaStream_t>(stream), dtype, kv, ld_kv, q, out, ld_out, frames, heads, S);

@@ -134,6 +134,13 @@ int spatial_attention_tc(cudaStream_t stream, int dtype, const void* qkv, int ld
 int pool_attention(cudaStream_t stream, int dtype, const void* kv, int ld_kv, const float* q,
                    void* out, int ld_out, int frames, int heads, int S);
 
+// The same pooling attention with the key / value projections collapsed into it (the query is one
+// learned probe): tokens [frames*S, D] (row stride ld) -> out [frames, D] = concat_h(W_v,h s_h + b_v,h)
+// with s_h = softmax_n(x_n . u_h)-weighted token sum; u [heads, D] fp32 = W_k,h^T q_h (q scaled),
+// wv [D, D] row-major in the activation dtype, bv [D] fp32.
+int pool_probe(cudaStream_t stream, int dtype, const void* tokens, int ld, const float* u, const void* wv, const float* bv,
+               void* out, int ld_out, int frames, int heads, int S);
+
 // out = cast(in)  (weight / bias packing helpers; n elements)
 int cast(cudaStream_t stream, int src_dtype, const void* src, int dst_dtype, void* dst, size_t n);
 

@@ -142,3 +142,16 @@ def pool_attention(kv: torch.Tensor, q: torch.Tensor, frames: int, heads: int, S
     N.check(N.load().sf_op_pool_attention(_stream(), sf_dtype(kv.dtype), kv.data_ptr(), kv.stride(0), q.data_ptr(),
                                           out.data_ptr(), out.stride(0), frames, heads, S), "sf_op_pool_attention")
     return out
+
+
+def pool_probe(tokens: torch.Tensor, u: torch.Tensor, wv: torch.Tensor, bv: torch.Tensor, frames: int, heads: int,
+               S: int) -> torch.Tensor:
+    """Pooling attention with a single probe, K/V projections collapsed: tokens [frames*S, D] -> [frames, D]."""
+    _req(tokens, u, wv, bv)
+    assert u.dtype == torch.float32 and bv.dtype == torch.float32 and wv.dtype == tokens.dtype
+    D = heads * 64
+    out = torch.empty(frames, D, dtype=tokens.dtype, device=tokens.device)
+    N.check(N.load().sf_op_pool_probe(_stream(), sf_dtype(tokens.dtype), tokens.data_ptr(), tokens.stride(0), u.data_ptr(),
+                                      wv.data_ptr(), bv.data_ptr(), out.data_ptr(), out.stride(0), frames, heads, S),
+            "sf_op_pool_probe")
+    return out

@@ -345,3 +345,26 @@ def test_pool_attention(frames, S):
     s = torch.einsum("hd,fhsd->fhs", q.view(H, 64), k).softmax(-1)
     ref = torch.einsum("fhs,fhsd->fhd", s, v).reshape(frames, D)
     _close(out, ref, torch.bfloat16, "pool attention", scale=2.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("frames,S", [(16, 196), (5, 49), (3, 1), (2, 400)])
+def test_pool_probe_matches_projected_attention(dtype, frames, S):
+    """Collapsed probe pooling == softmax(q . (W_k x + b_k)) (W_v x + b_v) per head, computed the long way in fp32."""
+    ops = _ops()
+    heads, D = 12, 768
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(frames * S, D, generator=g).to(DEV, dtype)
+    wk = (torch.randn(D, D, generator=g) * 0.05).to(DEV)
+    wv = (torch.randn(D, D, generator=g) * 0.05).to(DEV, dtype)
+    bk = torch.randn(D, generator=g).to(DEV)
+    bv = torch.randn(D, generator=g).to(DEV)
+    q = (torch.randn(D, generator=g) * 0.3).to(DEV)                  # already scaled probe query
+    u = torch.einsum("hdk,hd->hk", wk.view(heads, 64, D), q.view(heads, 64)).contiguous()
+    out = ops.pool_probe(x, u, wv, bv, frames, heads, S).float()
+    xf = x.float().view(frames, S, D)
+    k = (xf @ wk.t() + bk).view(frames, S, heads, 64)
+    v = (xf @ wv.float().t() + bv).view(frames, S, heads, 64)
+    p = torch.softmax(torch.einsum("fshd,hd->fhs", k, q.view(heads, 64)), dim=-1)
+    ref = torch.einsum("fhs,fshd->fhd", p, v).reshape(frames, D)
+    _close(out, ref, dtype, "pool_probe")
