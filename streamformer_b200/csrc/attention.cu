@@ -16,6 +16,7 @@
 
 #include "sf_kernels.h"
 #include "sf_ptx.cuh"
+#include "sf_tma.h"
 
 namespace sf {
 namespace {
@@ -216,6 +217,110 @@ __global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const Tempo
   T* obase = reinterpret_cast<T*>(a.out) + (site * a.Tq) * a.out_ld + h * kHd;
   finalize_store<T>(o, l_run, obase + static_cast<long>(i0 + g) * a.out_ld,
                     obase + static_cast<long>(i0 + g + 8) * a.out_ld, ok0, ok1, c);
+}
+
+// Fast path for the batch forward (no cache, all T <= 16 frames of a site in one 16-row tile): a
+// persistent warp walks (site, head) tasks with the NEXT task's Q, K and V tiles already in flight
+// (cp.async, two stages per warp), takes its Q fragments from shared memory with ldmatrix and sends
+// the output through the consumed Q tile so that it leaves as 16-byte stores.  The generic kernel
+// above spends 44 % of its samples waiting for the one load round trip each short-lived CTA makes
+// and keeps the LSU 59 % busy with 4-byte Q loads / output stores (profiles/r1_ncu_layer.md).
+template <typename T>
+__global__ void __launch_bounds__(kTWarps * 32, 4) temporal_attn_fast_kernel(const TemporalArgs a) {
+  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+  extern __shared__ __align__(128) uint8_t tsm[];   // [warp][stage][Q | K | V][16 x 128 B]
+  griddep_wait();
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  uint8_t* wbase = tsm + warp * (2 * 3 * 2048);
+  const long stride = static_cast<long>(gridDim.x) * kTWarps;
+  long task = static_cast<long>(blockIdx.x) * kTWarps + warp;
+  const T* qg = reinterpret_cast<const T*>(a.q);
+  const T* kg = reinterpret_cast<const T*>(a.k);
+  const T* vg = reinterpret_cast<const T*>(a.v);
+  auto issue = [&](long t, int stage) {
+    const int h = static_cast<int>(t % a.heads);
+    const long site = t / a.heads;
+    const T* qb = qg + (site * a.Tq) * a.q_ld + h * kHd;
+    const T* kb = kg + site * a.kv_site_stride + h * a.kv_head_stride;
+    const T* vb = vg + site * a.kv_site_stride + h * a.kv_head_stride;
+    uint8_t* st = wbase + stage * (3 * 2048);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = lane + 32 * i;
+      const int row = idx >> 3, ch = idx & 7;
+      const bool ok = row < a.Tq;
+      const long r = ok ? row : 0;
+      cp_async_16(st + tile_off(row, ch), qb + r * a.q_ld + ch * 8, ok);
+      cp_async_16(st + 2048 + tile_off(row, ch), kb + r * a.kv_row_stride + ch * 8, ok);
+      cp_async_16(st + 4096 + tile_off(row, ch), vb + r * a.kv_row_stride + ch * 8, ok);
+    }
+    cp_async_commit();
+  };
+  int stage = 0;
+  if (task < a.tasks) issue(task, 0);
+  for (; task < a.tasks; task += stride, stage ^= 1) {
+    const long next = task + stride;
+    if (next < a.tasks) {
+      issue(next, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    uint8_t* st = wbase + stage * (3 * 2048);
+    const uint32_t qs_u = smem_u32(st), ks_u = qs_u + 2048, vs_u = qs_u + 4096;
+    uint32_t qa[4][4];
+    {
+      const int mi = lane >> 3;
+      const int row = (lane & 7) + (mi & 1) * 8;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qa[ks], qs_u + tile_off(row, 2 * ks + (mi >> 1)));
+    }
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    qk_16keys<kBf16>(s0, s1, qa, ks_u, 0, lane);
+    const int lim0 = a.causal ? g : (a.Tk - 1);
+    const int lim1 = a.causal ? (g + 8) : (a.Tk - 1);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j0 = 2 * c + e, j1 = 8 + 2 * c + e;
+      s0[e] = (j0 < a.Tk && j0 <= lim0) ? s0[e] * a.scale_log2 : -INFINITY;
+      s0[2 + e] = (j0 < a.Tk && j0 <= lim1) ? s0[2 + e] * a.scale_log2 : -INFINITY;
+      s1[e] = (j1 < a.Tk && j1 <= lim0) ? s1[e] * a.scale_log2 : -INFINITY;
+      s1[2 + e] = (j1 < a.Tk && j1 <= lim1) ? s1[2 + e] * a.scale_log2 : -INFINITY;
+    }
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
+    uint32_t pa[4];
+    softmax_step<T>(s0, s1, m_run, l_run, o, pa);
+    pv_16keys<kBf16>(o, pa, vs_u, 0, lane);
+    float l0 = l_run[0], l1 = l_run[1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    __syncwarp();   // every lane has its Q fragments: the Q tile becomes the output staging tile
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      *reinterpret_cast<uint32_t*>(st + tile_off(g, d) + 4 * c) = Pack2<T>::pack(o[d][0] * i0, o[d][1] * i0);
+      *reinterpret_cast<uint32_t*>(st + tile_off(g + 8, d) + 4 * c) = Pack2<T>::pack(o[d][2] * i1, o[d][3] * i1);
+    }
+    __syncwarp();
+    const int h = static_cast<int>(task % a.heads);
+    const long site = task / a.heads;
+    T* obase = reinterpret_cast<T*>(a.out) + (site * a.Tq) * a.out_ld + h * kHd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = lane + 32 * i;
+      const int row = idx >> 3, ch = idx & 7;
+      if (row < a.Tq) *reinterpret_cast<uint4*>(obase + static_cast<long>(row) * a.out_ld + ch * 8) = *reinterpret_cast<const uint4*>(st + tile_off(row, ch));
+    }
+    __syncwarp();   // the tile is refilled two iterations from now
+  }
 }
 
 // K/V slices of the fresh QKV projection -> cache[site][head][pos0 + i][64]
@@ -677,6 +782,15 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
   const long blocks = (a.tasks + kTWarps - 1) / kTWarps;
   ProfScope ps(stream, kProfTemporalAttn, 4.0 * sites * heads * static_cast<double>(Tq) * Tk * kHd,
                2.0 * sites * heads * kHd * (2.0 * Tq + 2.0 * Tk));
+  static const bool fast_on = [] { const char* e = getenv("SF_TEMPORAL_FAST"); return !(e && e[0] == '0'); }();
+  if (fast_on && !kcache && Tq == Tk && Tq <= 16 && q_off == 0 && (ld_out % 8) == 0) {
+    const long max_blocks = static_cast<long>(num_sms()) * 4;
+    const size_t smem = static_cast<size_t>(kTWarps) * 2 * 3 * 2048;
+    LaunchCfg lf(dim3(static_cast<unsigned>(blocks < max_blocks ? blocks : max_blocks)), dim3(kTWarps * 32), smem, stream);
+    if (dtype == kBF16) cudaLaunchKernelEx(&lf.cfg, temporal_attn_fast_kernel<__nv_bfloat16>, a);
+    else cudaLaunchKernelEx(&lf.cfg, temporal_attn_fast_kernel<__half>, a);
+    return check_launch("temporal_attention");
+  }
   LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(kTWarps * 32), 0, stream);
   if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, temporal_attn_kernel<__nv_bfloat16>, a);
   else cudaLaunchKernelEx(&lc.cfg, temporal_attn_kernel<__half>, a);
