@@ -139,7 +139,7 @@ constexpr int kTWarps = 4;
 template <typename T>
 __global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const TemporalArgs a_in) {
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-  __shared__ __align__(128) uint8_t smem[kTWarps][2][16 * 128];  // per warp: K tile, V tile
+  __shared__ __align__(128) uint8_t smem[kTWarps][2][2][16 * 128];  // per warp: two stages of (K tile, V tile)
   griddep_wait();
   griddep_launch_dependents();
   TemporalArgs a = a_in;
@@ -166,9 +166,21 @@ __global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const Tempo
 
   const T* kbase = reinterpret_cast<const T*>(a.k) + site * a.kv_site_stride + h * a.kv_head_stride;
   const T* vbase = reinterpret_cast<const T*>(a.v) + site * a.kv_site_stride + h * a.kv_head_stride;
-  uint8_t* ks = smem[warp][0];
-  uint8_t* vs = smem[warp][1];
-  const uint32_t ks_u = smem_u32(ks), vs_u = smem_u32(vs);
+  // 16-key slabs are double-buffered: slab i+1 is in flight (cp.async) while slab i is consumed
+  auto issue_slab = [&](int kb0, int stage) {
+    uint8_t* ks = smem[warp][stage][0];
+    uint8_t* vs = smem[warp][stage][1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = lane + 32 * i;
+      const int row = idx >> 3, ch = idx & 7;
+      const bool ok = (kb0 + row) < a.Tk;
+      const long roff = static_cast<long>(ok ? kb0 + row : 0) * a.kv_row_stride + ch * 8;
+      cp_async_16(ks + tile_off(row, ch), kbase + roff, ok);
+      cp_async_16(vs + tile_off(row, ch), vbase + roff, ok);
+    }
+    cp_async_commit();
+  };
 
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   float o[8][4];
@@ -180,20 +192,18 @@ __global__ void __launch_bounds__(kTWarps * 32) temporal_attn_kernel(const Tempo
   int kmax = a.causal ? (a.q_off + last_q + 1) : a.Tk;
   if (kmax > a.Tk) kmax = a.Tk;
 
-  for (int kb0 = 0; kb0 < kmax; kb0 += 16) {
-    // stage K/V rows kb0..kb0+15 (zero-filled past Tk)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = lane + 32 * i;
-      const int row = idx >> 3, ch = idx & 7;
-      const bool ok = (kb0 + row) < a.Tk;
-      const long roff = static_cast<long>(ok ? kb0 + row : 0) * a.kv_row_stride + ch * 8;
-      cp_async_16(ks + tile_off(row, ch), kbase + roff, ok);
-      cp_async_16(vs + tile_off(row, ch), vbase + roff, ok);
+  if (kmax > 0) issue_slab(0, 0);
+  int stage = 0;
+  for (int kb0 = 0; kb0 < kmax; kb0 += 16, stage ^= 1) {
+    // K/V rows kb0..kb0+15 (zero-filled past Tk) are landing in `stage`; request the next slab first
+    if (kb0 + 16 < kmax) {
+      issue_slab(kb0 + 16, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    cp_async_commit();
-    cp_async_wait<0>();
     __syncwarp();
+    const uint32_t ks_u = smem_u32(smem[warp][stage][0]), vs_u = smem_u32(smem[warp][stage][1]);
 
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
     qk_16keys<kBf16>(s0, s1, qa, ks_u, 0, lane);
