@@ -5,6 +5,8 @@
 //     materialised permute copies at :962-971, 982-991, 1332-1346).
 //   * im2col for the 16x16/s16 patch-embedding conv (reference :336-350): pixels -> patch-major
 //     GEMM operand with K ordered (c, kh, kw), cast to the activation dtype on the fly.
+#include <stdlib.h>
+
 #include "sf_kernels.h"
 #include "sf_ptx.cuh"
 
@@ -233,8 +235,65 @@ im2col_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int BT, int C, 
   }
 }
 
+// Tiled variant: one CTA per (frame, patch row).  The P image rows x C channels of the strip are read
+// as whole pixel rows (fully coalesced, converted to T on the way into shared memory), then every
+// patch's K = C*P*P values leave as one contiguous output row — both sides of the copy move whole
+// cache lines (the gather kernel above reads 32-byte pieces 16 rows apart: 2.1 TB/s).
+template <typename PixT, typename T>
+__global__ void __launch_bounds__(256)
+im2col_strip_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int C, int H, int W, int P) {
+  extern __shared__ __align__(16) uint8_t strip_raw[];
+  T* strip = reinterpret_cast<T*>(strip_raw);                 // [C][P][W]
+  griddep_wait();
+  griddep_launch_dependents();
+  const int gw = W / P, gh = H / P;
+  const long bt = blockIdx.x / gh;
+  const int ph = blockIdx.x % gh;
+  const int wc = W >> 3;                                      // 8-pixel pieces per image row
+  const int pieces = C * P * wc;
+  for (int i = threadIdx.x; i < pieces; i += blockDim.x) {
+    const int x8 = i % wc, rowi = i / wc;                     // rowi = c * P + kh
+    const int c = rowi / P, kh = rowi % P;
+    const PixT* src = pix + ((bt * C + c) * H + (ph * P + kh)) * static_cast<long>(W) + x8 * 8;
+    float f[8];
+    load8<PixT>(src, f);
+    uint4 o;
+    o.x = Pack2<T>::pack(f[0], f[1]);
+    o.y = Pack2<T>::pack(f[2], f[3]);
+    o.z = Pack2<T>::pack(f[4], f[5]);
+    o.w = Pack2<T>::pack(f[6], f[7]);
+    *reinterpret_cast<uint4*>(strip + static_cast<long>(rowi) * W + x8 * 8) = o;
+  }
+  __syncthreads();
+  const int K = C * P * P;
+  const int kc = K >> 3;                                      // 8-element pieces per output row
+  const int pc = P >> 3;
+  const long m0 = (bt * gh + ph) * static_cast<long>(gw);
+  for (int i = threadIdx.x; i < gw * kc; i += blockDim.x) {
+    const int pw = i / kc, j = i % kc;
+    const int part = j % pc, rowi = j / pc;                   // rowi = c * P + kh
+    const uint4 v = *reinterpret_cast<const uint4*>(strip + static_cast<long>(rowi) * W + pw * P + part * 8);
+    *reinterpret_cast<uint4*>(out + (m0 + pw) * K + j * 8) = v;
+  }
+}
+
 template <typename PixT, typename T>
 int launch_im2col(cudaStream_t st, const void* pix, void* out, int BT, int C, int H, int W, int P) {
+  const size_t strip_bytes = static_cast<size_t>(C) * P * W * sizeof(T);
+  static const bool strip_on = [] { const char* e = getenv("SF_IM2COL_STRIP"); return !(e && e[0] == '0'); }();
+  if (strip_on && strip_bytes <= 48 * 1024 && (W % 8) == 0 && (P % 8) == 0) {
+    const long total = static_cast<long>(BT) * (H / P) * (W / P) * (C * P * P / 8);
+    {
+      ProfScope ps(st, kProfIm2col, 0.0, static_cast<double>(total) * 8 * (sizeof(PixT) + sizeof(T)));
+      LaunchCfg lc(dim3(static_cast<unsigned>(BT * (H / P))), dim3(256), strip_bytes, st);
+      cudaLaunchKernelEx(&lc.cfg, im2col_strip_kernel<PixT, T>, reinterpret_cast<const PixT*>(pix), reinterpret_cast<T*>(out),
+                         C, H, W, P);
+    }
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("im2col launch: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+  }
   const long total = static_cast<long>(BT) * (H / P) * (W / P) * (C * P * P / 8);
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 32) blocks = 148L * 32;
