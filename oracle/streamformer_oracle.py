@@ -196,14 +196,52 @@ def patch_embeddings(w: Dict[str, np.ndarray], cfg: OracleConfig, pixels: np.nda
     return linear(x, wt, w["embeddings.patch_embeddings.projection.bias"])
 
 
+def _cubic_aa_filter(x: np.ndarray, a: float = -0.5) -> np.ndarray:
+    """Keys cubic convolution kernel with a = -0.5, the filter of ATen's anti-aliased bicubic resize."""
+    x = np.abs(x)
+    near = ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0
+    far = (((x - 5.0) * x + 8.0) * x - 4.0) * a
+    return np.where(x < 1.0, near, np.where(x < 2.0, far, 0.0))
+
+
+def _aa_resize_matrix(in_size: int, out_size: int) -> np.ndarray:
+    """[out, in] weights of one separable pass of F.interpolate(mode="bicubic", antialias=True,
+    align_corners=False): support 2*max(scale,1) taps around centre scale*(i+0.5), weights normalised per
+    output sample (torch ATen UpSampleKernel `_compute_indices_weights_aa`; torch is the third-party
+    dependency the reference calls at R:402-407, pinned 2.5.1 in requirements.txt:26)."""
+    scale = in_size / out_size
+    support = 2.0 * scale if scale >= 1.0 else 2.0
+    inv = 1.0 / scale if scale >= 1.0 else 1.0
+    m = np.zeros((out_size, in_size), dtype=np.float64)
+    for i in range(out_size):
+        center = scale * (i + 0.5)
+        lo = max(int(center - support + 0.5), 0)
+        hi = min(int(center + support + 0.5), in_size)
+        j = np.arange(lo, hi)
+        wgt = _cubic_aa_filter((j - center + 0.5) * inv)
+        m[i, lo:hi] = wgt / wgt.sum()
+    return m
+
+
 def position_table(w: Dict[str, np.ndarray], cfg: OracleConfig, npatch: int, H: int, W: int) -> np.ndarray:
-    """interpolate_pos_encoding (R:380-411).  Only the identity branch (npatch == N and W == H) is
-    restated here; the bicubic-antialias branch is a PyTorch resampling filter the product also leaves
-    to PyTorch and is therefore outside the oracle."""
+    """interpolate_pos_encoding (R:380-411).  Identity when npatch == N and W == H; otherwise the
+    [M, M] table is resampled (bicubic, antialias) to size (w0, h0) = (W // P, H // P) — in THAT order,
+    as the reference passes it (R:389-401) — and flattened row-major, so for a non-square input the
+    table is laid out [w0, h0] while the patch tokens are laid out [H // P, W // P]."""
     pos = w["embeddings.position_embeddings"]
     if npatch == pos.shape[1] and W == H:
         return pos
-    raise NotImplementedError("oracle covers the default resolution only")
+    Np, D = pos.shape[1], pos.shape[2]
+    M = int(math.sqrt(Np))
+    assert Np == M * M
+    w0, h0 = W // cfg.patch_size, H // cfg.patch_size
+    grid = pos.reshape(M, M, D).astype(np.float64)
+    rows = _aa_resize_matrix(M, w0)            # first spatial axis  -> w0
+    cols = _aa_resize_matrix(M, h0)            # second spatial axis -> h0
+    out = np.einsum("im,mnd->ind", rows, grid)
+    out = np.einsum("jn,ind->ijd", cols, out)
+    assert out.shape[0] * out.shape[1] == npatch
+    return out.reshape(1, npatch, D).astype(F32)
 
 
 def embeddings(w: Dict[str, np.ndarray], cfg: OracleConfig, pixels: np.ndarray, past_frames: int = 0,

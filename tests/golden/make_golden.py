@@ -40,6 +40,20 @@ CASES = {
     # streaming: the twin run as 8+8 frames and as 16 x 1 frames, plus its one-shot forward
     "twin_stream": dict(model="twin", B=1, T=16, layers=2, causal=True, lora=True, style="stress", seed=7,
                         chunks=[[8, 8], [1] * 16]),
+    # BASELINE.json config 3 shape (64 appends of one frame, B > 1): the twin built with num_frames=64 so the
+    # reference can stream 64 frames at all (it raises at frame num_frames+1, KV:343-348), one-shot and 64 x 1
+    "twin_stream64": dict(model="twin", B=2, T=64, layers=2, causal=True, lora=True, style="stress", seed=8,
+                          num_frames=64, chunks=[[1] * 64]),
+    # the root copy one-shot at T = num_frames = 64 (what the cfg3 stream must equal)
+    "root_t64_nf64": dict(model="root", B=1, T=64, layers=2, causal=True, lora=False, style="stress", seed=9,
+                          num_frames=64),
+    # non-square input: bicubic-antialias position table in the reference's (w0, h0) order (R:380-411),
+    # im2col with H != W, spatial attention over 392 tokens
+    "nonsquare_224x448": dict(model="root", B=1, T=4, layers=2, causal=True, lora=False, style="stress", seed=10,
+                              H=224, W=448),
+    # lower resolution (down-sampling branch of the antialias filter), 49 tokens per frame
+    "lowres_112": dict(model="root", B=2, T=3, layers=2, causal=True, lora=False, style="stress", seed=11,
+                       H=112, W=112),
 }
 
 SUB_TOK, SUB_DIM = 14, 8  # last_hidden_state[..., ::14, ::8]
@@ -87,7 +101,7 @@ def run_case(name: str) -> None:
     case = CASES[name]
     ocfg = oracle_cfg(case)
     weights = O.make_weights(ocfg, seed=case["seed"], style=case["style"])
-    pixels = O.make_pixels(case["B"], case["T"], ocfg, seed=case["seed"])
+    pixels = O.make_pixels(case["B"], case["T"], ocfg, seed=case["seed"], H=case.get("H"), W=case.get("W"))
     out = {"case": json.dumps(case)}
     torch.manual_seed(0)
     torch.set_grad_enabled(False)

@@ -28,7 +28,7 @@ def case_config(case) -> O.OracleConfig:
 def case_inputs(case):
     cfg = case_config(case)
     w = O.make_weights(cfg, seed=case["seed"], style=case["style"])
-    px = O.make_pixels(case["B"], case["T"], cfg, seed=case["seed"])
+    px = O.make_pixels(case["B"], case["T"], cfg, seed=case["seed"], H=case.get("H"), W=case.get("W"))
     return cfg, w, px
 
 
