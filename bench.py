@@ -2,13 +2,15 @@
 """bench.py — StreamFormer encoder frames/sec on B200 (BASELINE.json metric) in the driver's contract.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA, sm_100a)
-    python bench.py --impl reference [--gpus N] [--steps K] ...    # reference arm: CPU oracle port
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # reference arm: the reference's own PyTorch
+                                                                   # classes on the host cores (baseline/_ref)
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # N > 1: one rank per GPU, NCCL
 
-A step = one encoder forward (patch embed -> 12 divided space-time blocks -> post-LN -> SigLIP
-pooling head) over one batch of synthetic clips [B,16,3,224,224] per GPU (BASELINE.json configs[1]:
-B=8, T=16, 224x224, bf16), followed for N>1 by the all-gather of pooler_output.
-Rank 0 prints ONE JSON line.
+A step = one encoder forward (patch embed -> 12 divided space-time blocks -> post-LN -> SigLIP pooling head)
+over one batch of synthetic clips [B,16,3,224,224] per GPU (BASELINE.json configs[1]: B=8, T=16, 224x224,
+bf16), followed for N>1 by the all-gather of pooler_output.  Rank 0 prints ONE JSON line.
+The other BASELINE configs (cfg3 streaming, cfg4 per-GPU shard of the global-256 step, cfg5 long clip) are
+measured in the same run and reported under "configs".
 """
 from __future__ import annotations
 
@@ -25,23 +27,22 @@ sys.path.insert(0, ROOT)
 
 METRIC = "encoder frames/sec at [B,16,3,224,224]"
 UNIT = "frames/s"
-# dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one cfg2 step
-# (per layer: 108.3 + 85.8 + 108.9 + 82.8 + 147.4 + 224.3 MB from profiles/r1_ncu_layer.md, x 12 layers;
-# embed and head GEMMs estimated at their algorithmic bytes, 0.25 GB)
-NCU_GEMM_TRAFFIC_BYTES = 12 * (108.3 + 85.8 + 108.9 + 82.8 + 147.4 + 224.3) * 1e6 + 0.25e9
+# geometry of the reference model (StreamformerConfig defaults)
+D, HEADS, MLP, PATCHES, KP = 768, 12, 3072, 196, 3 * 16 * 16
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="clips per GPU (configs[1]: 8)")
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg4 / cfg5 sub-measurements")
     ap.add_argument("--no-fold", action="store_true", help="run temporal out-proj and temporal_dense un-folded")
     return ap.parse_args()
 
@@ -55,39 +56,92 @@ def load_peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
-# ------------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_clip_seconds(layers: int, frames: int, repeats: int = 1):
-    """Time the numpy oracle (port of the reference forward) on one clip with all host threads."""
-    from oracle import streamformer_oracle as O
+# ------------------------------------------------------------------------------------- work accounting
+def flops_per_clip(T: int, layers: int) -> float:
+    """Algorithmic FLOPs of one clip (BASELINE.md §4 / SURVEY §8d: 2*M*N*K, full non-causal attention count,
+    no LoRA, un-folded reference graph): 790.5 G at T=16, 12 layers."""
+    M = T * PATCHES
+    per_layer = 2 * M * D * 3 * D * 2 + 2 * M * D * D * 3 + 2 * 2 * M * T * D + 2 * 2 * M * PATCHES * D + 2 * 2 * M * D * MLP
+    head = 2 * M * D * 2 * D + 2 * 2 * T * PATCHES * D + 2 * T * D * D + 2 * 2 * T * D * MLP
+    return float(2 * M * KP * D + layers * per_layer + head)
+
+
+def attention_block_flops_per_clip(T: int) -> float:
+    """One layer's space-time attention block incl. its projections, excl. the MLP (35.34 G at T=16)."""
+    M = T * PATCHES
+    return float(2 * M * D * 3 * D * 2 + 2 * M * D * D * 3 + 2 * 2 * M * T * D + 2 * 2 * M * PATCHES * D)
+
+
+# ------------------------------------------------------------------------------------- CPU arms
+def host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core regardless and reports the count."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def reference_model(layers: int):
+    """The UNMODIFIED reference classes from baseline/_ref (staged by baseline/stage_reference.py), random init
+    with non-trivial gates / time embeddings, eval, fp32.  None when the staged copy is absent."""
+    import torch
+    try:
+        from baseline.stage_reference import import_reference, stage
+        if not stage(quiet=True):
+            return None
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            Config, Model = import_reference()
+            torch.manual_seed(0)
+            model = Model(Config(num_hidden_layers=layers, enable_causal_temporal=True)).eval()
+        with torch.no_grad():
+            for layer in model.encoder.layer:
+                layer.temporal_attention_gating.uniform_(-1, 1)
+            model.embeddings.time_embeddings.normal_(0, 0.02)
+        return model
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] reference import failed: {e!r}", file=sys.stderr)
+        return None
+
+
+def cpu_forward_fn(layers: int, frames: int):
+    """(callable running one clip [1,T,3,224,224] on the host, kind, threads)."""
+    import torch
+    threads = host_threads()
+    model = reference_model(layers)
+    if model is not None:
+        px = torch.randn(1, frames, 3, 224, 224)
+
+        def run():
+            with torch.no_grad():
+                return model(px).pooler_output
+        return run, "reference", threads
+    from oracle import streamformer_oracle as O   # fallback: the numpy port (cpu_baseline leg only)
     cfg = O.OracleConfig(num_hidden_layers=layers)
     w = O.make_weights(cfg, seed=0)
     px = O.make_pixels(1, frames, cfg, seed=0)
-    ts = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        O.forward(w, cfg, px)
-        ts.append(time.perf_counter() - t0)
-    return ts
+    return (lambda: O.forward(w, cfg, px)), "port", threads
 
 
 def run_reference_arm(args):
-    """Reference arm for this tier: the reference's CPU implementation of the path.  The reference is
-    Python/PyTorch and cannot travel to the GPU box, so this times the oracle port (numpy, all host
-    threads) on a bounded sample of the same workload: one clip [1,T,3,224,224] per step."""
+    """Reference arm for this tier: the reference's own CPU implementation of the path — its PyTorch classes,
+    imported unmodified from baseline/_ref — on the box's host cores, one clip [1,T,3,224,224] per step
+    (a bounded sample of the workload), all host threads.  Rank 0 only; other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    run, kind, threads = cpu_forward_fn(args.layers, args.frames)
     budget_s = 240.0
-    from oracle import streamformer_oracle as O
-    cfg = O.OracleConfig(num_hidden_layers=args.layers)
-    w = O.make_weights(cfg, seed=0)
-    px = O.make_pixels(1, args.frames, cfg, seed=0)
     t_start = time.perf_counter()
     warm = 0
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):
         t0 = time.perf_counter()
-        O.forward(w, cfg, px)
+        run()
         warm += 1
         per = time.perf_counter() - t0
         if (time.perf_counter() - t_start) + per * (args.steps + 1) > budget_s:
@@ -95,20 +149,22 @@ def run_reference_arm(args):
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        O.forward(w, cfg, px)
+        run()
         times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+        if time.perf_counter() - t_start > budget_s:
             break
     total = sum(times)
     fps = args.frames * len(times) / total
+    what = ("the reference's TimesformerMultiTaskingModelSigLIP (unmodified, baseline/_ref), PyTorch eager fp32"
+            if kind == "reference" else "numpy port of the reference forward (baseline/_ref not staged)")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CPU oracle port of the reference forward, one clip [1,{args.frames},3,224,224] per step, "
-                               f"{args.layers} layers, fp32 numpy/BLAS on {cores} host threads"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} x 1 clip of {args.frames} frames"},
+        "config": {"workload": f"{what}, one clip [1,{args.frames},3,224,224] per step, {args.layers} layers, on {threads} "
+                               f"host threads (rank 0 only; the CPU arm does not scale with --gpus)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{len(times)} x 1 clip of {args.frames} frames, median {statistics.median(times):.2f} s/clip"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -169,14 +225,112 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- GPU arm
+def make_model(torch, layers, dev, dtype, num_frames=16, fold=True):
+    from streamformer_b200.modeling_timesformer_siglip import StreamformerConfig, TimesformerMultiTaskingModelSigLIP
+    cfg = StreamformerConfig(num_hidden_layers=layers, enable_causal_temporal=True, fold_temporal_proj=fold,
+                             num_frames=num_frames)
+    torch.manual_seed(0)
+    model = TimesformerMultiTaskingModelSigLIP(cfg)
+    with torch.no_grad():  # non-trivial gates / time embeddings (SURVEY §0.1)
+        for layer in model.encoder.layer:
+            layer.temporal_attention_gating.uniform_(-1, 1)
+        model.embeddings.time_embeddings.normal_(0, 0.02)
+    return model.to(dev, dtype).eval()
+
+
+def timed_steps(torch, fn, warm, reps):
+    """Per-step CUDA-event times [ms] of `reps` calls of fn(i) after `warm` untimed ones."""
+    for i in range(warm):
+        fn(i)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(reps):
+        fn(i)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
+
+
+def bench_cfg3(torch, N, args, dev, dtype, peaks):
+    """BASELINE configs[2]: streaming KV-cache path, 64 appends of one frame at B=4 (replicas only: the
+    state is per stream, so this runs on one GPU)."""
+    B, steps = 4, 64
+    model = make_model(torch, args.layers, dev, dtype, num_frames=steps)
+    frames = [torch.randn(B, 1, 3, 224, 224, device=dev, dtype=dtype) for _ in range(4)]
+    cache = model.new_kv_cache(B, max_frames=steps)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    totals, per_step, launches, host_us = [], None, 0, None
+    with torch.no_grad():
+        for r in range(4):          # round 0 = warm-up (captures the graph)
+            cache.reset()
+            torch.cuda.synchronize()
+            l0 = N.launch_count()
+            t0 = time.perf_counter()
+            ev[0].record()
+            for s in range(steps):
+                model(frames[s % 4], past_key_values=cache, use_cache=True)
+                ev[s + 1].record()
+            host = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            launches = N.launch_count() - l0
+            if r:
+                totals.append(ev[0].elapsed_time(ev[steps]))
+                per_step = [ev[s].elapsed_time(ev[s + 1]) for s in range(steps)]
+                host_us = host / steps * 1e6
+    tot = statistics.median(totals)
+    ms = tot / steps
+    # floor of a step: max(GEMM FLOPs at tensor peak, bytes that must move at HBM peak): the weights are read
+    # once per step (M = 784 rows cannot amortise them) + the K/V history of every layer, growing with the step
+    gemm_flops = flops_per_clip(1, args.layers) * B
+    weight_bytes = args.layers * (2 * 3 * D * D + 2 * D * D + 2 * D * MLP) * 2 + (2 * D * D + D * D + 2 * D * MLP + KP * D) * 2
+    kv_bytes_mean = args.layers * 2 * B * PATCHES * HEADS * 64 * 2 * (steps + 1) / 2
+    floor_ms = max(gemm_flops / (peaks["burst"] * 1e12), (weight_bytes + kv_bytes_mean) / (peaks["hbm"] * 1e9)) * 1e3
+    return {"workload": f"configs[2]: streaming KV cache, {steps} x (B={B}, T=1) appends, {args.layers} layers, CUDA-graph replay",
+            "frames_per_s": B * steps / tot * 1e3, "ms_per_step": ms,
+            "ms_step_1_16_32_64": [round(per_step[i], 4) for i in (0, 15, 31, steps - 1)],
+            "host_us_per_step": host_us, "gpu_launches_per_step": launches // steps, "graph_steps": cache.graph_launches,
+            "kv_cache_gb": 2 * args.layers * B * PATCHES * HEADS * steps * 64 * 2 / 2**30,
+            "roofline": {"bound": "max(tensor, hbm)", "floor_ms_per_step": floor_ms, "frac": floor_ms / ms,
+                         "gemm_ms_at_burst_peak": gemm_flops / (peaks["burst"] * 1e12) * 1e3,
+                         "weight_plus_mean_kv_bytes": weight_bytes + kv_bytes_mean,
+                         "note": "floor = max(step GEMM FLOPs / burst bf16 peak, (packed weights + mean K/V history) / HBM peak)"}}
+
+
+def bench_forward(torch, dist, N, args, dev, dtype, peaks, name, B, T, world, warm, reps):
+    """One-shot forward of B clips x T frames per GPU (+ all_gather of pooler_output at N > 1)."""
+    model = make_model(torch, args.layers, dev, dtype)
+    xs = [torch.randn(B, T, 3, 224, 224, device=dev, dtype=dtype) for _ in range(2)]
+    gathered = torch.empty(world * B, T, D, device=dev, dtype=dtype) if world > 1 else None
+    with torch.no_grad():
+        def fn(i):
+            out = model(xs[i % 2])
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out.pooler_output)
+        if world > 1:
+            dist.barrier()
+        ts = timed_steps(torch, fn, warm, reps)
+    t = torch.tensor([sum(ts)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / reps
+    fl = flops_per_clip(T, args.layers) * B
+    res = {"workload": name, "global_batch": world * B, "frames": T, "ms_per_step": ms,
+           "ms_per_step_median_rank0": statistics.median(ts), "frames_per_s": world * B * T / ms * 1e3,
+           "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peaks["burst"], "unit": "TFLOP/s",
+                        "frac": fl / (ms * 1e-3) / 1e12 / peaks["burst"],
+                        "note": "algorithmic FLOPs of the step (un-folded reference graph) per GPU / step time, vs burst bf16 peak"},
+           "mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30}
+    del model, xs
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
-    from oracle import streamformer_oracle as O  # only for flops accounting + cpu_baseline leg
     from streamformer_b200 import _native as N
-    from streamformer_b200.modeling_timesformer_siglip import StreamformerConfig, TimesformerMultiTaskingModelSigLIP
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,20 +346,15 @@ def run_ours(args):
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     B, T, K, W = args.batch, args.frames, args.steps, max(args.warmup, 3)
-    cfg = StreamformerConfig(num_hidden_layers=args.layers, enable_causal_temporal=True,
-                             fold_temporal_proj=not args.no_fold)
-    torch.manual_seed(0)
-    model = TimesformerMultiTaskingModelSigLIP(cfg)
-    with torch.no_grad():  # non-trivial gates / time embeddings (SURVEY §0.1)
-        for layer in model.encoder.layer:
-            layer.temporal_attention_gating.uniform_(-1, 1)
-        model.embeddings.time_embeddings.normal_(0, 0.02)
-    model = model.to(dev, dtype).eval()
+    model = make_model(torch, args.layers, dev, dtype, fold=not args.no_fold)
+    peaks = load_peaks()
 
-    S, D = 196, cfg.hidden_size
+    S = PATCHES
     NBUF = 4  # rotate inputs: 4 x 38.5 MB (bf16) > L2, and the per-step working set (~0.7 GB) >> 126 MB L2
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    host_f32 = [torch.randn(B, T, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
+    # e2e inputs: uint8 frames as a video decoder hands them over ([B,T,H,W,3]); the loader's
+    # ClipToTensor + Normalize(0.5, 0.5) runs inside the patch-embedding front end on the GPU
+    host_u8 = [torch.randint(0, 256, (B, T, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
     dev_in = [torch.randn(B, T, 3, 224, 224, device=dev, dtype=dtype) for _ in range(NBUF)]
     gathered = torch.empty(world * B, T, D, device=dev, dtype=dtype) if world > 1 else None
 
@@ -220,6 +369,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    gather_check = None
     with torch.no_grad():
         for i in range(W):
             step(i)
@@ -227,21 +377,42 @@ def run_ours(args):
         sampler = ClockSampler(local_rank)
         sampler.start()
         l0 = N.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         barrier()
-        e0.record()
+        ev[0].record()
         for i in range(K):
             step(i)
-        e1.record()
+            ev[i + 1].record()
         barrier()
         launches = N.launch_count() - l0
-        ms_total = e0.elapsed_time(e1)
+        ms_total = ev[0].elapsed_time(ev[K])
+        step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
         clocks = sampler.stop()
 
-        # ---- e2e: through the public API with HOST inputs (fp32 pinned, as the reference's loader
-        # hands them over), H2D + forward + D2H of pooler_output every step, double-buffered.
+        # ---- multi-rank correctness of the one exchange step (SURVEY §4 vi): every rank's slice of the
+        # gathered tensor is its local pooler_output, and all ranks hold the same gathered tensor
+        if world > 1:
+            out = step(0)
+            torch.cuda.synchronize()
+            ok = torch.equal(gathered[rank * B:(rank + 1) * B], out.pooler_output)
+            for r in range(world):
+                ok = ok and bool(torch.isfinite(gathered[r * B:(r + 1) * B].float()).all())
+            digest = gathered.float().double().sum().reshape(1)
+            digests = [torch.empty_like(digest) for _ in range(world)]
+            dist.all_gather(digests, digest)
+            same = all(float(d) == float(digests[0]) for d in digests)
+            distinct = len({float(gathered[r * B:(r + 1) * B].float().double().sum()) for r in range(world)}) == world
+            flag = torch.tensor([int(ok and same and distinct)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            gather_check = {"ok": bool(int(flag)), "what": "gathered[r*B:(r+1)*B] == local pooler_output on every rank, finite, "
+                            "identical checksum on all ranks, ranks' slices differ (different seeds)"}
+            if not gather_check["ok"]:
+                raise SystemExit(f"rank {rank}: all_gather(pooler_output) check failed")
+
+        # ---- e2e: through the public API with HOST inputs: pinned uint8 frames -> H2D (copy stream,
+        # double-buffered) -> model(pixel_values) -> pooler_output D2H, every step
         copy_stream = torch.cuda.Stream(dev)
-        stage = [torch.empty(B, T, 3, 224, 224, device=dev, dtype=torch.float32) for _ in range(2)]
+        stage = [torch.empty(B, T, 224, 224, 3, device=dev, dtype=torch.uint8) for _ in range(2)]
         host_out = [torch.empty(B, T, D, dtype=dtype).pin_memory() for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
@@ -252,14 +423,14 @@ def run_ours(args):
                 consumed[j].record(main)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[0])
-                stage[0].copy_(host_f32[0], non_blocking=True)
+                stage[0].copy_(host_u8[0], non_blocking=True)
                 ready[0].record(copy_stream)
             for i in range(n):
                 cur, nxt = i % 2, (i + 1) % 2
                 if i + 1 < n:
                     with torch.cuda.stream(copy_stream):
                         copy_stream.wait_event(consumed[nxt])
-                        stage[nxt].copy_(host_f32[(i + 1) % 2], non_blocking=True)
+                        stage[nxt].copy_(host_u8[(i + 1) % 2], non_blocking=True)
                         ready[nxt].record(copy_stream)
                 main.wait_event(ready[cur])
                 out = model(stage[cur])
@@ -280,8 +451,8 @@ def run_ours(args):
         # ---- per-kernel-class durations, measured in situ (CUDA events around every launch of a
         # full step, on the launching stream) in a separate instrumented pass
         prof = phases = None
+        PK = min(K, 5)
         if rank == 0:
-            PK = min(K, 5)
             torch.cuda.synchronize()
             N.profile(True)
             for i in range(PK):
@@ -306,32 +477,62 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
 
+    del dev_in, stage
+    torch.cuda.empty_cache()
+    configs = {}
+    if not args.no_configs and (B, T) == (8, 16):
+        # BASELINE.md §5 protocol for configs[1]: >= 10 warm-up, >= 50 timed, median of per-step event times
+        with torch.no_grad():
+            xs = [torch.randn(B, T, 3, 224, 224, device=dev, dtype=dtype) for _ in range(NBUF)]
+            ts = timed_steps(torch, lambda i: model(xs[i % NBUF]), 10, 50) if rank == 0 else None
+            del xs
+        if rank == 0:
+            med = statistics.median(ts)
+            configs["cfg2_median"] = {"workload": "configs[1]: B=8 T=16, 10 warm-up + 50 timed forwards, median per-step CUDA-event time (rank 0, no gather)",
+                                      "ms_per_step_median": med, "frames_per_s": B * T / med * 1e3,
+                                      "frac_of_burst": flops_per_clip(T, args.layers) * B / (med * 1e-3) / 1e12 / peaks["burst"]}
+        del model
+        torch.cuda.empty_cache()
+        # configs[3]: per-GPU shard of the global-256 step (32 clips / GPU; at N=8 the global batch is 256)
+        configs["cfg4_shard"] = bench_forward(torch, dist, N, args, dev, dtype, peaks,
+                                              f"configs[3]: batch-sharded forward, 32 clips/GPU x {world} GPU(s) (global B={32 * world}), T=16, "
+                                              "forward + all_gather(pooler_output); backward not included in this line", 32, 16, world, 2, 6)
+        if world == 1:
+            configs["cfg5_long_clip"] = bench_forward(torch, dist, N, args, dev, dtype, peaks,
+                                                      "configs[4]: long clip B=2 T=128 224x224 bf16, 1 GPU", 2, 128, 1, 3, 10)
+            configs["cfg3_streaming"] = bench_cfg3(torch, N, args, dev, dtype, peaks)
+
     if rank == 0:
-        peaks = load_peaks()
         frames_per_step = world * B * T
         value = frames_per_step * K / (ms_total / 1e3)
         e2e_value = frames_per_step * K / (ms_e2e / 1e3)
-        ocfg = O.OracleConfig(num_hidden_layers=args.layers)
-        algo_flops_step = O.flops_per_clip(ocfg, T) * B  # per GPU
+        algo_flops_step = flops_per_clip(T, args.layers) * B  # per GPU
         gemm = prof["gemm"]
         gemm_tflops = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
         step_kernel_ms = sum(v["ms"] for v in prof.values())
+        # the timed region is K steps of a few ms: a burst, not the multi-second / power-limited regime the
+        # sustained peak was measured under -> burst peak unless the region ran for >= 2 s
+        long_run = ms_total >= 2000.0
+        peak = peaks["sustained"] if long_run else peaks["burst"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")
+        if os.path.exists(tpath) and (B, T, args.layers) == (8, 16, 12):
+            traffic = json.load(open(tpath))
         roofline = {
             "bound": "tensor", "kernel": "gemm_tcgen05_kernel",
-            "achieved": gemm_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
-            "frac": gemm_tflops / peaks["sustained"],
-            "peak_kind": "bf16_tflops_sustained, " + peaks["source"] + " — kernel timed inside a long step",
-            "frac_of_burst": gemm_tflops / peaks["burst"],
+            "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
+            "peak_kind": ("bf16_tflops_sustained" if long_run else "bf16_tflops (burst)") + ", " + peaks["source"]
+                         + f"; timed region {ms_total / 1e3:.2f} s",
+            "frac_of_burst": gemm_tflops / peaks["burst"], "frac_of_sustained": gemm_tflops / peaks["sustained"],
             "flops_per_step_executed": gemm["flops"], "gemm_ms_per_step": gemm["ms"], "gemm_launches_per_step": gemm["launches"],
             "gemm_share_of_kernel_time": gemm["ms"] / step_kernel_ms if step_kernel_ms else None,
-            "traffic": NCU_GEMM_TRAFFIC_BYTES if (B, T, args.layers) == (8, 16, 12) else None,
-            "traffic_note": "dram read+write of the 77 GEMM launches of one cfg2 step, from the ncu --set full capture "
-                            "of one layer (profiles/r1_ncu_layer.md) x 12 + embed/head; algorithmic bytes "
-                            f"{gemm['bytes'] / 1e9:.2f} GB",
-            "achieved_unit_note": "executed FLOPs of all GEMM launches of a step / their summed durations",
-
-            "step_algorithmic_tflops": algo_flops_step * world / (ms_total / K * 1e-3) / 1e12 / world,
-            "step_frac_of_sustained": algo_flops_step / (ms_total / K * 1e-3) / 1e12 / peaks["sustained"],
+            "traffic": traffic["dram_bytes_per_step"] if traffic else None,
+            "traffic_note": (traffic["how"] if traffic else "no ncu --set full capture of this build committed") +
+                            f"; algorithmic bytes {gemm['bytes'] / 1e9:.2f} GB",
+            "achieved_unit_note": "executed FLOPs of all GEMM launches of a step / their summed durations (CUDA events around "
+                                  "every launch, on the launching stream)",
+            "step_algorithmic_tflops": algo_flops_step / (ms_total / K * 1e-3) / 1e12,
+            "step_frac_of_burst": algo_flops_step / (ms_total / K * 1e-3) / 1e12 / peaks["burst"],
             "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in prof.items() if v["launches"]},
         }
         # BASELINE.json's second metric: tensor-pipe fraction of the space-time attention block of one
@@ -339,7 +540,7 @@ def run_ours(args):
         # attention + out-proj; SURVEY 8d: 35.34 GFLOP per clip and layer algorithmic, un-folded)
         ab = phases["attention_block"]
         ab_ms = ab["ms"] / (args.layers * PK)      # per layer (a layer contributes two timed spans in this mode)
-        ab_algo = O.attention_block_flops_per_clip(ocfg, T) * B
+        ab_algo = attention_block_flops_per_clip(T) * B
         ab_exec = ab_algo - (2.0 * B * T * S * D * D if not args.no_fold else 0.0)
         attention_block = {
             "ms_per_layer": ab_ms, "layers_timed": args.layers * PK,
@@ -356,13 +557,18 @@ def run_ours(args):
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            ts = cpu_oracle_clip_seconds(args.layers, T, repeats=1)
-            cpu = {"value": T / ts[0], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"1 clip [1,{T},3,224,224], {args.layers} layers, numpy fp32 oracle, {ts[0]:.1f} s"}
+            run, kind, threads = cpu_forward_fn(args.layers, T)
+            run()                                    # warm-up (lazy init, page-in)
+            t0 = time.perf_counter()
+            run()
+            dt = time.perf_counter() - t0
+            cpu = {"value": T / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"1 clip [1,{T},3,224,224], {args.layers} layers, fp32, {dt:.1f} s after one warm-up clip "
+                             + ("(the reference's own PyTorch classes from baseline/_ref)" if kind == "reference" else "(numpy port)")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
+            "ms_per_step": ms_total / K, "ms_per_step_median": statistics.median(step_ms), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"configs[1]: single-GPU encoder forward B={B} T={T} 224x224 {args.dtype}, "
                                    f"{args.layers} layers, per GPU; N>1 adds all_gather(pooler_output)",
                        "global_batch": world * B, "frames": T, "parallelism": f"dp{world}",
@@ -371,16 +577,19 @@ def run_ours(args):
                        "fold_temporal_proj": not args.no_fold, "weights": "random init (no network for checkpoints)"},
             "roofline": roofline,
             "attention_block": attention_block,
+            "configs": configs,
+            "gather_check": gather_check,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * T * 3 * 224 * 224 * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * T * 3 * 224 * 224,
                     "d2h_bytes_per_step": B * T * D * 2, "ms_per_step": ms_e2e / K,
-                    "note": "fp32 pinned host clips -> H2D (copy stream, double-buffered) -> model(pixel_values) -> "
-                            "pooler_output D2H, every step"},
+                    "note": "pinned uint8 host frames [B,T,224,224,3] (decoder layout) -> H2D (copy stream, double-buffered) -> "
+                            "model(pixel_values): normalise(0.5,0.5) + patch embed on the GPU -> pooler_output D2H, every step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

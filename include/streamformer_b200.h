@@ -38,7 +38,10 @@ typedef enum sf_status {
   SF_ERR_WORKSPACE = -5  /* caller-provided workspace too small */
 } sf_status;
 
-typedef enum sf_dtype { SF_BF16 = 0, SF_F16 = 1, SF_F32 = 2 } sf_dtype;
+/* SF_U8 / SF_U8_HWC are pixel formats only (planar [B,T,C,H,W] / interleaved [B,T,H,W,C] uint8 frames,
+ * normalised on the GPU: the input edge of extract_oad_feature.py:42-48, 124-130 and
+ * datasets/kinetics_sparse.py:110-118 moved behind the boundary) */
+typedef enum sf_dtype { SF_BF16 = 0, SF_F16 = 1, SF_F32 = 2, SF_U8 = 3, SF_U8_HWC = 4 } sf_dtype;
 typedef enum sf_act { SF_ACT_NONE = 0, SF_ACT_GELU = 1, SF_ACT_GELU_TANH = 2 } sf_act;
 typedef enum sf_rowmap { SF_ROW_IDENTITY = 0, SF_ROW_BTN_TO_BNT = 1, SF_ROW_BNT_TO_BTN = 2 } sf_rowmap;
 
@@ -80,7 +83,9 @@ uint64_t sf_launch_count(void);
 
 /* Library-wide switches.  "gemm_chain": 1 runs GEMMs that follow each other over the same rows
  * (out-proj -> fc1 -> fc2 -> next QKV ...) as one persistent launch with in-kernel row dependencies,
- * 0 one launch per GEMM, -1 the default (SF_GEMM_CHAIN environment variable, off). */
+ * 0 one launch per GEMM, -1 the default (SF_GEMM_CHAIN environment variable, off).
+ * "stream_graph": 0 serves streaming steps with direct launches, 1 from the captured CUDA graph, -1 the
+ * default (SF_STREAM_GRAPH environment variable, on). */
 int sf_set_option(const char* name, int value);
 
 /* In-situ profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.
@@ -103,16 +108,22 @@ int sf_profile_collect_phases(double* ms, long long* count, int n_phases);
 int sf_create(const sf_config* cfg, int device, sf_ctx** out);
 int sf_destroy(sf_ctx* ctx);
 /* replaces load_state_dict / from_pretrained weight materialisation; may be called again after an
- * optimiser step to re-pack. Optional LoRA tensors (…qkv_lora_{a,b}.weight, …dense_lora_{a,b}.weight,
+ * optimiser step to re-pack.  Parameter groups bind independently — embeddings.*, encoder.layer.{i}.*,
+ * post_layernorm.*, head.* — so a sub-module composed inside another model (downstream/AR/models/
+ * modeling_timesformer_video_classification.py:42-56) binds only what it owns; an entry point whose
+ * group is absent fails with SF_ERR_STATE. Optional LoRA tensors (…qkv_lora_{a,b}.weight, …dense_lora_{a,b}.weight,
  * …siglip.py:632-647, 731-746) are merged W + B.A. */
 int sf_bind_weights(sf_ctx* ctx, void* stream, const sf_weight_desc* w, int n);
+/* replaces the loaders' ClipToTensor + Normalize(mean, std) for uint8 pixels (extract_oad_feature.py:42-48):
+ * pixel -> (x / 255 - mean[c]) / std[c], evaluated in fp32 in that order.  Default 0.5 / 0.5; n <= 4. */
+int sf_set_pixel_norm(sf_ctx* ctx, const float* mean, const float* std, int n);
 /* interpolated position table for a non-default resolution (…siglip.py:380-411): fp32 [S, D] */
 int sf_set_pos_embed(sf_ctx* ctx, void* stream, const float* pos, int S);
 
 /* ---- full forward ------------------------------------------------------------------------ */
 int sf_workspace_bytes(const sf_ctx* ctx, int B, int T, int H, int W, size_t* out);
 /* replaces TimesformerMultiTaskingModelSigLIP.forward (…siglip.py:1299-1354).
- *   pixels        [B, T, C, H, W], pixels_dtype in {bf16, f16, f32}
+ *   pixels        [B, T, C, H, W], pixels_dtype in {bf16, f16, f32, u8}; or [B, T, H, W, C] with SF_U8_HWC
  *   last_hidden   [B, T, S, D]  activation dtype            (last_hidden_state)
  *   pooler        [B, T, D]     activation dtype            (pooler_output)
  *   hidden_states NULL or L+1 device pointers, each [B, S*T, D] (rows (b,n,t)), filled in order
@@ -131,6 +142,10 @@ int sf_kv_create(sf_ctx* ctx, int B, int S, int max_frames, int time_horizon, sf
 int sf_kv_reset(sf_kv* kv);
 int sf_kv_destroy(sf_kv* kv);
 int sf_kv_seq_len(const sf_kv* kv);
+/* block-level streaming (sf_embed_forward + sf_layer_forward with a cache): every layer of a step appends
+ * at the same position; the caller advances the cache by the step's frames once, after the last layer
+ * (sf_forward_stream does this itself) */
+int sf_kv_advance(sf_kv* kv, int frames);
 int sf_kv_capacity(const sf_kv* kv);
 /* steps of this cache that were served by replaying a captured CUDA graph (see sf_forward_stream) */
 long long sf_kv_graph_launches(const sf_kv* kv);
@@ -139,8 +154,9 @@ long long sf_kv_graph_launches(const sf_kv* kv);
  * From the second call with the same (B, T_new, H, W, dtype, workspace) on, the step is replayed
  * from a CUDA graph captured once: its kernels read the stream position from a device counter the
  * graph itself advances, so every step of every stream reuses one executable graph and the host
- * cost per step is two D2D staging copies + one graph launch (SF_STREAM_GRAPH=0 disables;
- * hidden_states != NULL and the profiling modes use direct launches). */
+ * cost per step is the D2D staging copies (pixels in; last_hidden, pooler and, when asked for, the L+1
+ * hidden states out) + one graph launch (SF_STREAM_GRAPH=0 / sf_set_option("stream_graph", 0) disable;
+ * the profiling modes use direct launches). */
 int sf_forward_stream(sf_ctx* ctx, void* stream, sf_kv* kv, const void* pixels, int pixels_dtype,
                       int B, int T_new, int H, int W, void* last_hidden, void* pooler,
                       void* const* hidden_states, void* workspace, size_t workspace_bytes);
@@ -155,6 +171,13 @@ int sf_embed_forward(sf_ctx* ctx, void* stream, const void* pixels, int pixels_d
 int sf_layer_forward(sf_ctx* ctx, void* stream, int layer, const void* x_in, void* x_out, int B,
                      int T, int S, sf_kv* kv, float* attn_probs, void* workspace,
                      size_t workspace_bytes);
+/* TimesformerEncoder.forward (…siglip.py:1019-1063): all layers over x_in [B, S*T, D].  hidden_states NULL
+ * (result in x_out, which may not alias x_in unless the model has one layer) or L+1 pointers of which
+ * [1..L] receive the layer outputs ([0] is the caller's x_in, not written; x_out is ignored then);
+ * attentions as sf_forward; kv NULL or a cache, advanced by T once all layers ran. */
+int sf_encoder_forward(sf_ctx* ctx, void* stream, const void* x_in, int B, int T, int S, sf_kv* kv,
+                       void* x_out, void* const* hidden_states, void* const* attentions, void* workspace,
+                       size_t workspace_bytes);
 /* post_layernorm + (b,n,t)->(b,t,n) (…siglip.py:1330-1346): x [B, S*T, D] -> [B, T, S, D] */
 int sf_final_norm(sf_ctx* ctx, void* stream, const void* x, int B, int T, int S, void* last_hidden);
 /* TimesformerSiglipMultiheadAttentionPoolingHead.forward (…siglip.py:1141-1154):

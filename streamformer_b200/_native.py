@@ -13,17 +13,17 @@ from typing import Optional, Sequence
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libstreamformer_b200.so")
 
-SF_BF16, SF_F16, SF_F32 = 0, 1, 2
+SF_BF16, SF_F16, SF_F32, SF_U8, SF_U8_HWC = 0, 1, 2, 3, 4
 SF_ACT_NONE, SF_ACT_GELU, SF_ACT_GELU_TANH = 0, 1, 2
 SF_ROW_IDENTITY, SF_ROW_BTN_TO_BNT, SF_ROW_BNT_TO_BTN = 0, 1, 2
 
 # every symbol include/streamformer_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "sf_last_error", "sf_version", "sf_launch_count", "sf_set_option", "sf_profile", "sf_profile_collect", "sf_profile_collect_phases",
-    "sf_create", "sf_destroy", "sf_bind_weights", "sf_set_pos_embed",
+    "sf_create", "sf_destroy", "sf_bind_weights", "sf_set_pos_embed", "sf_set_pixel_norm",
     "sf_workspace_bytes", "sf_forward",
-    "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_kv_graph_launches", "sf_forward_stream",
-    "sf_embed_forward", "sf_layer_forward", "sf_final_norm", "sf_head_forward",
+    "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_kv_advance", "sf_kv_graph_launches", "sf_forward_stream",
+    "sf_embed_forward", "sf_layer_forward", "sf_encoder_forward", "sf_final_norm", "sf_head_forward",
     "sf_op_gemm", "sf_op_layernorm", "sf_op_im2col", "sf_op_temporal_attention", "sf_op_kv_append",
     "sf_op_spatial_attention", "sf_op_pool_attention", "sf_op_pool_probe", "sf_op_rowstats", "sf_op_gemm_stats_parts",
 ]
@@ -86,6 +86,7 @@ def load() -> C.CDLL:
     lib.sf_destroy.argtypes = [vp]
     lib.sf_bind_weights.argtypes = [vp, vp, C.POINTER(SfWeightDesc), i]
     lib.sf_set_pos_embed.argtypes = [vp, vp, vp, i]
+    lib.sf_set_pixel_norm.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), i]
     lib.sf_workspace_bytes.argtypes = [vp, i, i, i, i, C.POINTER(C.c_size_t)]
     lib.sf_forward.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, C.c_size_t]
     lib.sf_kv_create.argtypes = [vp, i, i, i, i, C.POINTER(vp)]
@@ -93,10 +94,12 @@ def load() -> C.CDLL:
     lib.sf_kv_destroy.argtypes = [vp]
     lib.sf_kv_seq_len.argtypes = [vp]
     lib.sf_kv_capacity.argtypes = [vp]
+    lib.sf_kv_advance.argtypes = [vp, i]
     lib.sf_kv_graph_launches.argtypes = [vp]
     lib.sf_forward_stream.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, vp, C.POINTER(vp), vp, C.c_size_t]
     lib.sf_embed_forward.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp, vp, C.c_size_t]
     lib.sf_layer_forward.argtypes = [vp, vp, i, vp, vp, i, i, i, vp, vp, vp, C.c_size_t]
+    lib.sf_encoder_forward.argtypes = [vp, vp, vp, i, i, i, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, C.c_size_t]
     lib.sf_final_norm.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.sf_head_forward.argtypes = [vp, vp, vp, i, i, vp, vp, C.c_size_t]
     lib.sf_op_gemm.argtypes = [vp, i, vp, i, vp, i, vp, i, i, i, i, C.POINTER(SfGemmEpilogue)]

@@ -201,10 +201,36 @@ __device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
   }
 }
 
+template <>
+__device__ __forceinline__ void load8<uint8_t>(const uint8_t* p, float (&f)[8]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[j] = static_cast<float>((u.x >> (8 * j)) & 0xffu);
+    f[4 + j] = static_cast<float>((u.y >> (8 * j)) & 0xffu);
+  }
+}
+
+// uint8 frames are normalised on the way in: (x / 255 - mean[c]) / std[c], in fp32 and in exactly this
+// order — ClipToTensor (x / 255) then Normalize (sub mean, div std) of the reference's loaders
+// (extract_oad_feature.py:42-48, datasets/kinetics_sparse.py:110-118) — so the result is bit-identical
+// to handing the loader's fp32 tensor to the float path.  IEEE division, no reciprocal shortcuts.
+struct PixNorm {
+  float mean[4], std[4];
+};
+template <typename PixT>
+__device__ __forceinline__ void normalise8(float (&f)[8], const PixNorm& nm, int c) {
+  if constexpr (sizeof(PixT) == 1) {
+    const float m = nm.mean[c], sd = nm.std[c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __fdiv_rn(__fsub_rn(__fdiv_rn(f[j], 255.0f), m), sd);
+  }
+}
+
 // one thread = 8 consecutive kw of one (patch row m, channel c, kernel row kh)
 template <typename PixT, typename T>
 __global__ void __launch_bounds__(256)
-im2col_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int BT, int C, int H, int W, int P) {
+im2col_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int BT, int C, int H, int W, int P, PixNorm nm) {
   griddep_wait();
   griddep_launch_dependents();
   const int gw = W / P, gh = H / P;
@@ -226,6 +252,7 @@ im2col_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int BT, int C, 
     const PixT* src = pix + ((bt * C + c) * H + (ph * P + kh)) * static_cast<long>(W) + pw * P + part * 8;
     float f[8];
     load8<PixT>(src, f);
+    normalise8<PixT>(f, nm, c);
     uint4 o;
     o.x = Pack2<T>::pack(f[0], f[1]);
     o.y = Pack2<T>::pack(f[2], f[3]);
@@ -241,7 +268,7 @@ im2col_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int BT, int C, 
 // cache lines (the gather kernel above reads 32-byte pieces 16 rows apart: 2.1 TB/s).
 template <typename PixT, typename T>
 __global__ void __launch_bounds__(256)
-im2col_strip_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int C, int H, int W, int P) {
+im2col_strip_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int C, int H, int W, int P, PixNorm nm) {
   extern __shared__ __align__(16) uint8_t strip_raw[];
   T* strip = reinterpret_cast<T*>(strip_raw);                 // [C][P][W]
   griddep_wait();
@@ -257,6 +284,7 @@ im2col_strip_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int C, in
     const PixT* src = pix + ((bt * C + c) * H + (ph * P + kh)) * static_cast<long>(W) + x8 * 8;
     float f[8];
     load8<PixT>(src, f);
+    normalise8<PixT>(f, nm, c);
     uint4 o;
     o.x = Pack2<T>::pack(f[0], f[1]);
     o.y = Pack2<T>::pack(f[2], f[3]);
@@ -277,8 +305,76 @@ im2col_strip_kernel(const PixT* __restrict__ pix, T* __restrict__ out, int C, in
   }
 }
 
+// Interleaved uint8 frames [BT, H, W, C] (what a video decoder hands over): the P image rows of a patch
+// row are ONE contiguous run of P*W*C bytes, read with 16-byte loads, normalised and scattered into the
+// same [C][P][W] shared-memory strip; the write side is identical to the planar kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_strip_hwc_kernel(const uint8_t* __restrict__ pix, T* __restrict__ out, int C, int H, int W, int P, PixNorm nm) {
+  extern __shared__ __align__(16) uint8_t strip_raw[];
+  T* strip = reinterpret_cast<T*>(strip_raw);                 // [C][P][W]
+  griddep_wait();
+  griddep_launch_dependents();
+  const int gw = W / P, gh = H / P;
+  const long bt = blockIdx.x / gh;
+  const int ph = blockIdx.x % gh;
+  const int row_bytes = W * C;
+  const int total = P * row_bytes;                            // multiple of 16: P % 8 == 0 and W % 8 == 0
+  const uint8_t* src = pix + (bt * H + static_cast<long>(ph) * P) * row_bytes;
+  for (int i = threadIdx.x * 16; i < total; i += blockDim.x * 16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + i);
+    const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int e = i + j;
+      const int kh = e / row_bytes, r = e - kh * row_bytes;
+      const int x = r / C, c = r - x * C;
+      const float raw = static_cast<float>((wds[j >> 2] >> (8 * (j & 3))) & 0xffu);
+      const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(raw, 255.0f), nm.mean[c]), nm.std[c]);
+      strip[(static_cast<long>(c) * P + kh) * W + x] = static_cast<T>(v);
+    }
+  }
+  __syncthreads();
+  const int K = C * P * P;
+  const int kc = K >> 3;
+  const int pc = P >> 3;
+  const long m0 = (bt * gh + ph) * static_cast<long>(gw);
+  for (int i = threadIdx.x; i < gw * kc; i += blockDim.x) {
+    const int pw = i / kc, j = i % kc;
+    const int part = j % pc, rowi = j / pc;
+    const uint4 v = *reinterpret_cast<const uint4*>(strip + static_cast<long>(rowi) * W + pw * P + part * 8);
+    *reinterpret_cast<uint4*>(out + (m0 + pw) * K + j * 8) = v;
+  }
+}
+
+constexpr size_t kStripMaxBytes = 200 * 1024;   // opt-in dynamic shared memory (227 KB per CTA on sm_100)
+
+template <typename T>
+int launch_im2col_hwc(cudaStream_t st, const void* pix, void* out, int BT, int C, int H, int W, int P, const PixNorm& nm) {
+  const size_t strip_bytes = static_cast<size_t>(C) * P * W * sizeof(T);
+  if (strip_bytes > kStripMaxBytes || (W % 8) || (P % 8) || C > 4) {
+    set_error("im2col: interleaved uint8 frames need C <= 4 and a %zu-byte strip <= %zu bytes (W=%d)", strip_bytes, kStripMaxBytes, W);
+    return -1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(im2col_strip_hwc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kStripMaxBytes));
+    attr_set = true;
+  }
+  const long total = static_cast<long>(BT) * (H / P) * (W / P) * (C * P * P / 8);
+  {
+    ProfScope ps(st, kProfIm2col, 0.0, static_cast<double>(total) * 8 * (1 + sizeof(T)));
+    LaunchCfg lc(dim3(static_cast<unsigned>(BT * (H / P))), dim3(256), strip_bytes, st);
+    cudaLaunchKernelEx(&lc.cfg, im2col_strip_hwc_kernel<T>, reinterpret_cast<const uint8_t*>(pix), reinterpret_cast<T*>(out), C, H, W, P, nm);
+  }
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("im2col launch: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
 template <typename PixT, typename T>
-int launch_im2col(cudaStream_t st, const void* pix, void* out, int BT, int C, int H, int W, int P) {
+int launch_im2col(cudaStream_t st, const void* pix, void* out, int BT, int C, int H, int W, int P, const PixNorm& nm) {
   const size_t strip_bytes = static_cast<size_t>(C) * P * W * sizeof(T);
   static const bool strip_on = [] { const char* e = getenv("SF_IM2COL_STRIP"); return !(e && e[0] == '0'); }();
   if (strip_on && strip_bytes <= 48 * 1024 && (W % 8) == 0 && (P % 8) == 0) {
@@ -287,7 +383,7 @@ int launch_im2col(cudaStream_t st, const void* pix, void* out, int BT, int C, in
       ProfScope ps(st, kProfIm2col, 0.0, static_cast<double>(total) * 8 * (sizeof(PixT) + sizeof(T)));
       LaunchCfg lc(dim3(static_cast<unsigned>(BT * (H / P))), dim3(256), strip_bytes, st);
       cudaLaunchKernelEx(&lc.cfg, im2col_strip_kernel<PixT, T>, reinterpret_cast<const PixT*>(pix), reinterpret_cast<T*>(out),
-                         C, H, W, P);
+                         C, H, W, P, nm);
     }
     count_launch();
     cudaError_t e = cudaGetLastError();
@@ -302,7 +398,7 @@ int launch_im2col(cudaStream_t st, const void* pix, void* out, int BT, int C, in
     ProfScope ps(st, kProfIm2col, 0.0, static_cast<double>(total) * 8 * (sizeof(PixT) + sizeof(T)));
     LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st);
     cudaLaunchKernelEx(&lc.cfg, im2col_kernel<PixT, T>, reinterpret_cast<const PixT*>(pix), reinterpret_cast<T*>(out),
-                       BT, C, H, W, P);
+                       BT, C, H, W, P, nm);
   }
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -352,18 +448,27 @@ int rowstats(cudaStream_t stream, int dtype, const void* x, int ldx, int M, int 
 }
 
 int im2col_patches(cudaStream_t stream, int pix_dtype, const void* pixels, int act_dtype, void* out,
-                   int BT, int C, int H, int W, int P) {
+                   int BT, int C, int H, int W, int P, const float* mean, const float* std) {
   if (BT <= 0) return 0;
+  PixNorm nm;
+  for (int i = 0; i < 4; ++i) { nm.mean[i] = mean ? mean[i] : 0.5f; nm.std[i] = std ? std[i] : 0.5f; }
+  if ((pix_dtype == kU8 || pix_dtype == kU8HWC) && C > 4) { set_error("im2col: uint8 frames support at most 4 channels"); return -1; }
   if ((P % 8) || (H % P) || (W % P)) {
     set_error("im2col: patch size must be a multiple of 8 and divide H, W (H=%d W=%d P=%d)", H, W, P);
     return -1;
   }
-#define SF_IM2COL(PT, AT) return launch_im2col<PT, AT>(stream, pixels, out, BT, C, H, W, P)
+#define SF_IM2COL(PT, AT) return launch_im2col<PT, AT>(stream, pixels, out, BT, C, H, W, P, nm)
+  if (pix_dtype == kU8HWC) {
+    if (act_dtype == kBF16) return launch_im2col_hwc<__nv_bfloat16>(stream, pixels, out, BT, C, H, W, P, nm);
+    if (act_dtype == kF16) return launch_im2col_hwc<__half>(stream, pixels, out, BT, C, H, W, P, nm);
+  }
   if (act_dtype == kBF16) {
+    if (pix_dtype == kU8) SF_IM2COL(uint8_t, __nv_bfloat16);
     if (pix_dtype == kF32) SF_IM2COL(float, __nv_bfloat16);
     if (pix_dtype == kBF16) SF_IM2COL(__nv_bfloat16, __nv_bfloat16);
     if (pix_dtype == kF16) SF_IM2COL(__half, __nv_bfloat16);
   } else if (act_dtype == kF16) {
+    if (pix_dtype == kU8) SF_IM2COL(uint8_t, __half);
     if (pix_dtype == kF32) SF_IM2COL(float, __half);
     if (pix_dtype == kBF16) SF_IM2COL(__nv_bfloat16, __half);
     if (pix_dtype == kF16) SF_IM2COL(__half, __half);

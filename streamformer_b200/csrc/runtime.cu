@@ -35,6 +35,20 @@ using namespace sf;
 
 namespace {
 
+// Makes the context's device current for the duration of a C-ABI call and restores the caller's
+// device afterwards (the host may drive several GPUs from one thread).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // ------------------------------------------------------------------ bind-time fp32 helper kernels
 __global__ void lora_merge_kernel(float* __restrict__ W, const float* __restrict__ A,
                                   const float* __restrict__ Bm, int O, int I, int R) {
@@ -149,6 +163,14 @@ struct sf_ctx {
   int device = 0;
   int D = 0, H = 0, I = 0, L = 0, S0 = 0, Kp = 0;  // hidden, heads, mlp, layers, default sites, patch K
   bool bound = false;
+  // which parameter groups the last sf_bind_weights call found (a stand-alone TimesformerEncoder /
+  // embeddings / pooling head binds only its own tensors)
+  bool have_embed = false, have_post = false, have_head = false;
+  std::vector<char> have_layer;
+  // uint8 pixels: (x / 255 - mean[c]) / std[c] inside im2col (Normalize(0.5, 0.5) of the reference's
+  // loaders: extract_oad_feature.py:42-48, datasets/kinetics_sparse.py:110-118)
+  float pix_mean[4] = {0.5f, 0.5f, 0.5f, 0.5f}, pix_std[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+  int pos_epoch = 0;           // bumped whenever pos_alt is re-allocated (captured graphs hold its address)
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   std::vector<LayerW> layers;
@@ -173,10 +195,12 @@ struct sf_ctx {
 struct StreamGraph {
   cudaGraphExec_t exec = nullptr;
   int B = 0, T = 0, H = 0, W = 0, pix_dtype = 0;
-  bool pooler = false;
+  bool pooler = false, hidden = false;
   void* ws = nullptr; size_t ws_bytes = 0;
-  uint8_t* stage = nullptr;                 // pixels | last_hidden | pooler staging (graph-owned addresses)
-  size_t pix_bytes = 0, lh_bytes = 0, pool_bytes = 0;
+  uint8_t* stage = nullptr;                 // pixels | last_hidden | pooler | L+1 hidden states (graph-owned addresses)
+  size_t pix_bytes = 0, lh_bytes = 0, pool_bytes = 0, hs_bytes = 0;
+  std::vector<void*> hs_ptrs;
+  int pos_epoch = 0;                        // sf_ctx::pos_epoch at capture time
   int calls = 0;                            // eager calls seen with this key (capture happens on the 2nd)
   int kernels = 0;                          // kernel nodes in the graph (for sf_launch_count)
 };
@@ -397,7 +421,8 @@ int run_embed(sf_ctx* c, cudaStream_t st, const void* pixels, int pix_dtype, int
     return SF_ERR_STATE;
   }
   const long M = static_cast<long>(B) * T * S;
-  SF_CHECK(im2col_patches(st, pix_dtype, pixels, dt, patches, B * T, C, Hh, Ww, P));
+  if (!c->have_embed) { set_error("embedding weights are not bound to this context"); return SF_ERR_STATE; }
+  SF_CHECK(im2col_patches(st, pix_dtype, pixels, dt, patches, B * T, C, Hh, Ww, P, c->pix_mean, c->pix_std));
   GemmEpilogue e = epi_bias(c->patch_b);
   e.row_map = kRowBTNtoBNT; e.T = T; e.S = S;
   e.pos = pos;
@@ -416,6 +441,7 @@ int run_head(sf_ctx* c, cudaStream_t st, const void* tokens, int frames, int S, 
   const int D = c->D, I = c->I, H = c->H, dt = c->cfg.dtype;
   const size_t es = 2;
   const long M = static_cast<long>(frames) * S;
+  if (!c->have_head) { set_error("pooling-head weights are not bound to this context"); return SF_ERR_STATE; }
   void* kvbuf = b.take(M * 2 * D * es);
   void* pc = b.take(static_cast<size_t>(frames) * D * es);
   void* r = b.take(static_cast<size_t>(frames) * D * es);
@@ -465,13 +491,22 @@ int check_shape(const sf_ctx* c, int B, int T, int Hh, int Ww) {
   return 0;
 }
 
+int check_groups(const sf_ctx* c, bool embed, int l0, int l1, bool post, bool head) {
+  if (embed && !c->have_embed) { set_error("embedding weights are not bound to this context"); return SF_ERR_STATE; }
+  for (int l = l0; l < l1; ++l)
+    if (l < 0 || l >= c->L || !c->have_layer[l]) { set_error("weights of encoder.layer.%d are not bound to this context", l); return SF_ERR_STATE; }
+  if (post && !c->have_post) { set_error("post_layernorm weights are not bound to this context"); return SF_ERR_STATE; }
+  if (head && !c->have_head) { set_error("pooling-head weights are not bound to this context"); return SF_ERR_STATE; }
+  return 0;
+}
+
 int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int pix_dtype, int B, int T,
                  int Hh, int Ww, void* last_hidden, void* pooler, void* const* hidden_states,
                  void* const* attentions, void* ws, size_t ws_bytes, bool dev_seen = false) {
   // dev_seen: being captured into a streaming CUDA graph — the kernels take the stream position
   // from kv->d_seen at run time and the host-side counter is advanced by the caller
   SF_CHECK(check_shape(c, B, T, Hh, Ww));
-  SF_CUDA(cudaSetDevice(c->device));
+  SF_CHECK(check_groups(c, true, 0, c->L, true, pooler != nullptr));
   const int P = c->cfg.patch_size, D = c->D;
   const int S = (Hh / P) * (Ww / P);
   const long M = static_cast<long>(B) * T * S;
@@ -549,9 +584,10 @@ __global__ void add_int_kernel(int* p, int v) {
   *p += v;
 }
 
+int g_stream_graph_opt = -1;   // sf_set_option("stream_graph", v): -1 environment default, 0 off, 1 on
 bool stream_graphs_enabled() {
-  static const bool on = [] { const char* e = getenv("SF_STREAM_GRAPH"); return !(e && e[0] == '0'); }();
-  return on;
+  static const bool env_on = [] { const char* e = getenv("SF_STREAM_GRAPH"); return !(e && e[0] == '0'); }();
+  return g_stream_graph_opt < 0 ? env_on : g_stream_graph_opt != 0;
 }
 
 void destroy_graph(StreamGraph& g) {
@@ -563,7 +599,7 @@ void destroy_graph(StreamGraph& g) {
 // returns 1 when the step was served by a graph launch, 0 when the caller must launch directly,
 // < 0 on error
 int try_stream_graph(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int pix_dtype, int B, int T, int Hh,
-                     int Ww, void* last_hidden, void* pooler, void* ws, size_t ws_bytes) {
+                     int Ww, void* last_hidden, void* pooler, void* const* hidden_states, void* ws, size_t ws_bytes) {
   if (!stream_graphs_enabled() || kv->graphs_disabled || prof_enabled() || phase_prof_enabled()) return 0;
   SF_CHECK(check_shape(c, B, T, Hh, Ww));
   const int P = c->cfg.patch_size, D = c->D;
@@ -571,15 +607,17 @@ int try_stream_graph(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, 
   if (kv->B != B || kv->S != S || kv->seen + T > kv->cap) return 0;   // the direct path reports the error
   StreamGraph* g = nullptr;
   for (auto& it : kv->graphs)
-    if (it.B == B && it.T == T && it.H == Hh && it.W == Ww && it.pix_dtype == pix_dtype && it.pooler == (pooler != nullptr)) g = &it;
+    if (it.B == B && it.T == T && it.H == Hh && it.W == Ww && it.pix_dtype == pix_dtype && it.pooler == (pooler != nullptr) &&
+        it.hidden == (hidden_states != nullptr)) g = &it;
   if (!g) {
     if (kv->graphs.size() >= 8) return 0;
     StreamGraph n;
     n.B = B; n.T = T; n.H = Hh; n.W = Ww; n.pix_dtype = pix_dtype; n.pooler = pooler != nullptr;
+    n.hidden = hidden_states != nullptr;
     kv->graphs.push_back(n);
     g = &kv->graphs.back();
   }
-  if (g->exec && (g->ws != ws || g->ws_bytes != ws_bytes)) {   // workspace was re-allocated: re-capture
+  if (g->exec && (g->ws != ws || g->ws_bytes != ws_bytes || g->pos_epoch != c->pos_epoch)) {   // workspace or position table was re-allocated: re-capture
     cudaGraphExecDestroy(g->exec);
     g->exec = nullptr;
     g->calls = 1;
@@ -589,13 +627,17 @@ int try_stream_graph(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, 
     // first call with this key runs eagerly (lazy one-time initialisation inside the launchers
     // must not happen under capture); the second one captures
     if (g->calls++ == 0) return 0;
-    SF_CUDA(cudaSetDevice(c->device));
     if (!g->stage) {
       const size_t al = 256;
       g->pix_bytes = (static_cast<size_t>(B) * T * c->cfg.num_channels * Hh * Ww * dtype_size(pix_dtype) + al - 1) / al * al;
       g->lh_bytes = (static_cast<size_t>(B) * T * S * D * 2 + al - 1) / al * al;
       g->pool_bytes = (static_cast<size_t>(B) * T * D * 2 + al - 1) / al * al;
-      SF_CUDA(cudaMalloc(&g->stage, g->pix_bytes + g->lh_bytes + g->pool_bytes));
+      g->hs_bytes = g->hidden ? g->lh_bytes : 0;     // one [B, S*T, D] tensor per layer boundary (the VideoQA tower
+                                                     // always asks for them, …timesformer_encoder.py:1536)
+      SF_CUDA(cudaMalloc(&g->stage, g->pix_bytes + g->lh_bytes + g->pool_bytes + g->hs_bytes * (c->L + 1)));
+      g->hs_ptrs.clear();
+      for (int l = 0; g->hidden && l <= c->L; ++l)
+        g->hs_ptrs.push_back(g->stage + g->pix_bytes + g->lh_bytes + g->pool_bytes + g->hs_bytes * l);
     }
     cudaGraph_t graph = nullptr;
     const uint64_t l0 = launch_count();
@@ -611,7 +653,8 @@ int try_stream_graph(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, 
     cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) return give_up("cudaStreamBeginCapture", e, 0);
     int rc = forward_impl(c, cs, kv, g->stage, pix_dtype, B, T, Hh, Ww, g->stage + g->pix_bytes,
-                          pooler ? g->stage + g->pix_bytes + g->lh_bytes : nullptr, nullptr, nullptr, ws, ws_bytes, true);
+                          pooler ? g->stage + g->pix_bytes + g->lh_bytes : nullptr, g->hidden ? g->hs_ptrs.data() : nullptr,
+                          nullptr, ws, ws_bytes, true);
     if (rc == 0) {
       LaunchCfg lc(dim3(1), dim3(1), 0, cs);
       if (cudaLaunchKernelEx(&lc.cfg, add_int_kernel, kv->d_seen, T) != cudaSuccess) rc = SF_ERR_CUDA;
@@ -628,7 +671,7 @@ int try_stream_graph(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, 
       g->exec = nullptr;
       return give_up("cudaGraphInstantiate", e, 0);
     }
-    g->ws = ws; g->ws_bytes = ws_bytes;
+    g->ws = ws; g->ws_bytes = ws_bytes; g->pos_epoch = c->pos_epoch;
     g->kernels = static_cast<int>(launch_count() - l0);   // counted while capturing; they run in the launch below
     just_captured = true;
   }
@@ -646,6 +689,8 @@ int try_stream_graph(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, 
   if (pooler)
     SF_CUDA(cudaMemcpyAsync(pooler, g->stage + g->pix_bytes + g->lh_bytes, static_cast<size_t>(B) * T * D * 2,
                             cudaMemcpyDeviceToDevice, st));
+  for (int l = 0; g->hidden && l <= c->L; ++l)
+    SF_CUDA(cudaMemcpyAsync(hidden_states[l], g->hs_ptrs[l], static_cast<size_t>(B) * T * S * D * 2, cudaMemcpyDeviceToDevice, st));
   kv->seen += T;
   kv->graph_launches += 1;
   return 1;
@@ -736,8 +781,8 @@ struct Binder {
   int mat_ln(const std::string& wname, const std::string& aname, const std::string& bname, const std::string& biasname,
              const float* gamma, const float* beta, long O, long I, void** w_out, float** bias_out, float** colsum_out) {
     SF_CHECK(load_f32(wname, aname, bname, O, I));
-    float* bias_raw = nullptr;
-    SF_CHECK(vec(biasname, O, &bias_raw));
+    float* bias_raw = nullptr;   // config.qkv_bias=False: the Linear has no bias (ln_fold_kernel takes nullptr)
+    if (find(biasname, false)) SF_CHECK(vec(biasname, O, &bias_raw));
     *w_out = arena.take(O * I * 2);
     *bias_out = static_cast<float*>(arena.take(O * sizeof(float)));
     *colsum_out = static_cast<float*>(arena.take(O * sizeof(float)));
@@ -773,6 +818,7 @@ const char* sf_version(void) { return "streamformer_b200 0.1 (sm_100a)"; }
 uint64_t sf_launch_count(void) { return launch_count(); }
 int sf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_chain") == 0) { set_gemm_chain(value); return 0; }
+  if (name && strcmp(name, "stream_graph") == 0) { g_stream_graph_opt = value; return 0; }
   set_error("sf_set_option: unknown option '%s'", name ? name : "(null)");
   return SF_ERR_INVALID;
 }
@@ -800,7 +846,7 @@ int sf_create(const sf_config* cfg, int device, sf_ctx** out) {
               cfg->image_size, cfg->hidden_size, cfg->intermediate_size);
     return SF_ERR_INVALID;
   }
-  SF_CUDA(cudaSetDevice(device));
+  DeviceGuard dg(device);
   int major = 0;
   SF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
   if (major != 10) {
@@ -815,12 +861,14 @@ int sf_create(const sf_config* cfg, int device, sf_ctx** out) {
   const int g = cfg->image_size / cfg->patch_size;
   c->S0 = g * g;
   c->layers.resize(c->L);
+  c->have_layer.assign(c->L, 0);
   *out = c;
   return 0;
 }
 
 int sf_destroy(sf_ctx* c) {
   if (!c) return 0;
+  DeviceGuard dg(c->device);
   if (c->arena) cudaFree(c->arena);
   if (c->pos_alt) cudaFree(c->pos_alt);
   delete c;
@@ -830,7 +878,7 @@ int sf_destroy(sf_ctx* c) {
 int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
   if (!c || !w) { set_error("sf_bind_weights: null argument"); return SF_ERR_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  SF_CUDA(cudaSetDevice(c->device));
+  DeviceGuard dg(c->device);
   Binder b;
   b.c = c; b.st = st;
   for (int i = 0; i < n; ++i) {
@@ -850,12 +898,30 @@ int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
   SF_CUDA(cudaMalloc(&scratch_mem, b.scratch_elems * 3 * sizeof(float)));
   for (int i = 0; i < 3; ++i) b.scratch[i] = scratch_mem + i * b.scratch_elems;
 
+  // Parameter groups are bound independently: the full model brings all of them; a stand-alone
+  // TimesformerEmbeddingsSigLIP / TimesformerEncoder / TimesformerLayerSigLIP / pooling head composed
+  // inside someone else's PreTrainedModel (downstream/AR/models/modeling_timesformer_video_classification.py:42-56,
+  // models/modeling_timesformer_siglip_adapter.py:481-482) brings only its own.
+  c->bound = false;
+  c->have_embed = b.find("embeddings.patch_embeddings.projection.weight", false) != nullptr;
+  c->have_post = b.find("post_layernorm.weight", false) != nullptr;
+  c->have_head = b.find("head.probe", false) != nullptr;
+  bool any = c->have_embed || c->have_post || c->have_head;
+  for (int l = 0; l < c->L; ++l) {
+    c->have_layer[l] = b.find("encoder.layer." + std::to_string(l) + ".attention.attention.qkv.weight", false) != nullptr;
+    any = any || c->have_layer[l];
+  }
+  if (!any) { set_error("sf_bind_weights: none of the %d tensors belongs to the encoder (names as in the reference state dict)", n); cudaFree(scratch_mem); return SF_ERR_INVALID; }
+
   auto body = [&]() -> int {
+    if (c->have_embed) {
     SF_CHECK(b.mat("embeddings.patch_embeddings.projection.weight", D, K, &c->patch_w));
     SF_CHECK(b.vec("embeddings.patch_embeddings.projection.bias", D, &c->patch_b));
     SF_CHECK(b.vec("embeddings.position_embeddings", static_cast<long>(c->S0) * D, &c->pos));
     SF_CHECK(b.vec("embeddings.time_embeddings", static_cast<long>(c->cfg.num_frames) * D, &c->time_emb));
+    }
     for (int l = 0; l < c->L; ++l) {
+      if (!c->have_layer[l]) continue;
       LayerW& lw = c->layers[l];
       const std::string p = "encoder.layer." + std::to_string(l) + ".";
       SF_CHECK(b.vec(p + "temporal_attention_gating", 1, &lw.gate));
@@ -900,10 +966,12 @@ int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
       SF_CHECK(b.mat(p + "output.dense.weight", D, I, &lw.fc2_w));
       SF_CHECK(b.vec(p + "output.dense.bias", D, &lw.fc2_b));
     }
+    if (c->have_post) {
     SF_CHECK(b.vec("post_layernorm.weight", D, &c->post_g));
     SF_CHECK(b.vec("post_layernorm.bias", D, &c->post_b));
+    }
     // pooling head: in_proj rows [0,D) = W_q, [D,3D) = W_k;W_v (…siglip.py:1135-1137)
-    {
+    if (c->have_head) {
       const sf_weight_desc* ipw = b.find("head.attention.in_proj_weight");
       const sf_weight_desc* ipb = b.find("head.attention.in_proj_bias");
       const sf_weight_desc* probe = b.find("head.probe");
@@ -936,6 +1004,7 @@ int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
                                                                                    static_cast<int>(D));
       count_launch();
     }
+    if (c->have_head) {
     SF_CHECK(b.mat("head.attention.out_proj.weight", D, D, &c->head_out_w));
     SF_CHECK(b.vec("head.attention.out_proj.bias", D, &c->head_out_b));
     SF_CHECK(b.vec("head.layernorm.weight", D, &c->head_ln_g));
@@ -944,12 +1013,17 @@ int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
     SF_CHECK(b.vec("head.mlp.fc1.bias", I, &c->head_fc1_b));
     SF_CHECK(b.mat("head.mlp.fc2.weight", D, I, &c->head_fc2_w));
     SF_CHECK(b.vec("head.mlp.fc2.bias", D, &c->head_fc2_b));
+    }
     if (b.arena.overflow) { set_error("sf_bind_weights: internal arena too small (%zu > %zu)", b.arena.off, b.arena.size); return SF_ERR_STATE; }
     return 0;
   };
   int rc = body();
   cudaError_t e = cudaStreamSynchronize(st);  // scratch is freed below; binding is not a hot path
   cudaFree(scratch_mem);
+  if (rc || e != cudaSuccess) {
+    c->have_embed = c->have_post = c->have_head = false;
+    c->have_layer.assign(c->L, 0);
+  }
   if (rc) return rc;
   if (e != cudaSuccess) { set_error("sf_bind_weights: %s", cudaGetErrorString(e)); return SF_ERR_CUDA; }
   c->bound = true;
@@ -958,11 +1032,14 @@ int sf_bind_weights(sf_ctx* c, void* stream, const sf_weight_desc* w, int n) {
 
 int sf_set_pos_embed(sf_ctx* c, void* stream, const float* pos, int S) {
   if (!c || !pos || S <= 0) { set_error("sf_set_pos_embed: bad argument"); return SF_ERR_INVALID; }
-  SF_CUDA(cudaSetDevice(c->device));
+  DeviceGuard dg(c->device);
   if (c->pos_alt_S != S) {
-    if (c->pos_alt) { cudaFree(c->pos_alt); c->pos_alt = nullptr; }
+    // captured streaming graphs hold the old table's address: the epoch makes them re-capture; the old
+    // table may still be read by work in flight on the stream, so it is released only after a sync
+    if (c->pos_alt) { cudaStreamSynchronize(static_cast<cudaStream_t>(stream)); cudaFree(c->pos_alt); c->pos_alt = nullptr; }
     SF_CUDA(cudaMalloc(&c->pos_alt, static_cast<size_t>(S) * c->D * sizeof(float)));
     c->pos_alt_S = S;
+    ++c->pos_epoch;
   }
   SF_CUDA(cudaMemcpyAsync(c->pos_alt, pos, static_cast<size_t>(S) * c->D * sizeof(float), cudaMemcpyDeviceToDevice,
                           static_cast<cudaStream_t>(stream)));
@@ -984,13 +1061,14 @@ int sf_forward(sf_ctx* c, void* stream, const void* pixels, int pixels_dtype, in
                void* last_hidden, void* pooler, void* const* hidden_states, void* const* attentions,
                void* workspace, size_t workspace_bytes) {
   if (!c || !pixels || !last_hidden) { set_error("sf_forward: null argument"); return SF_ERR_INVALID; }
+  DeviceGuard dg(c->device);
   return forward_impl(c, static_cast<cudaStream_t>(stream), nullptr, pixels, pixels_dtype, B, T, Hh, Ww, last_hidden,
                       pooler, hidden_states, attentions, workspace, workspace_bytes);
 }
 
 int sf_kv_create(sf_ctx* c, int B, int S, int max_frames, int time_horizon, sf_kv** out) {
   if (!c || !out || B <= 0 || S <= 0 || max_frames <= 0) { set_error("sf_kv_create: bad argument"); return SF_ERR_INVALID; }
-  SF_CUDA(cudaSetDevice(c->device));
+  DeviceGuard dg(c->device);
   sf_kv* kv = new sf_kv();
   kv->ctx = c; kv->B = B; kv->S = S; kv->cap = max_frames; kv->horizon = time_horizon;
   kv->kv_bytes = static_cast<size_t>(B) * S * c->H * max_frames * 64 * 2;
@@ -1013,11 +1091,28 @@ int sf_kv_reset(sf_kv* kv) {
 }
 int sf_kv_destroy(sf_kv* kv) {
   if (!kv) return 0;
+  DeviceGuard dg(kv->ctx ? kv->ctx->device : 0);
   for (auto& g : kv->graphs) destroy_graph(g);
   if (kv->mem) cudaFree(kv->mem);
   if (kv->d_seen) cudaFree(kv->d_seen);
   if (kv->cap_stream) cudaStreamDestroy(kv->cap_stream);
   delete kv;
+  return 0;
+}
+int sf_kv_advance(sf_kv* kv, int frames) {
+  if (!kv || frames < 0 || kv->seen + frames > kv->cap) { set_error("sf_kv_advance: bad argument or cache overflow"); return SF_ERR_INVALID; }
+  kv->seen += frames;
+  kv->seen_dirty = true;
+  return 0;
+}
+int sf_set_pixel_norm(sf_ctx* c, const float* mean, const float* std, int n) {
+  if (!c || !mean || !std || n <= 0 || n > 4) { set_error("sf_set_pixel_norm: bad argument"); return SF_ERR_INVALID; }
+  for (int i = 0; i < 4; ++i) {
+    c->pix_mean[i] = mean[i < n ? i : n - 1];
+    c->pix_std[i] = std[i < n ? i : n - 1];
+    if (!(c->pix_std[i] > 0.f)) { set_error("sf_set_pixel_norm: std must be positive"); return SF_ERR_INVALID; }
+  }
+  ++c->pos_epoch;   // captured streaming graphs baked the old constants in: re-capture
   return 0;
 }
 int sf_kv_seq_len(const sf_kv* kv) { return kv ? kv->seen : 0; }
@@ -1028,9 +1123,11 @@ int sf_forward_stream(sf_ctx* c, void* stream, sf_kv* kv, const void* pixels, in
                       int Hh, int Ww, void* last_hidden, void* pooler, void* const* hidden_states, void* workspace,
                       size_t workspace_bytes) {
   if (!c || !kv || !pixels || !last_hidden) { set_error("sf_forward_stream: null argument"); return SF_ERR_INVALID; }
-  if (!hidden_states) {
+  if (kv->ctx != c) { set_error("sf_forward_stream: the cache belongs to another context"); return SF_ERR_INVALID; }
+  DeviceGuard dg(c->device);
+  {
     const int served = try_stream_graph(c, static_cast<cudaStream_t>(stream), kv, pixels, pixels_dtype, B, T_new, Hh, Ww,
-                                        last_hidden, pooler, workspace, workspace_bytes);
+                                        last_hidden, pooler, hidden_states, workspace, workspace_bytes);
     if (served != 0) return served < 0 ? served : 0;
   }
   return forward_impl(c, static_cast<cudaStream_t>(stream), kv, pixels, pixels_dtype, B, T_new, Hh, Ww, last_hidden,
@@ -1040,6 +1137,7 @@ int sf_forward_stream(sf_ctx* c, void* stream, sf_kv* kv, const void* pixels, in
 int sf_embed_forward(sf_ctx* c, void* stream, const void* pixels, int pixels_dtype, int B, int T, int Hh, int Ww,
                      int time_off, int time_total, void* x_out, void* workspace, size_t workspace_bytes) {
   if (!c || !pixels || !x_out) { set_error("sf_embed_forward: null argument"); return SF_ERR_INVALID; }
+  DeviceGuard dg(c->device);
   SF_CHECK(check_shape(c, B, T, Hh, Ww));
   const int P = c->cfg.patch_size;
   const long M = static_cast<long>(B) * T * (Hh / P) * (Ww / P);
@@ -1057,6 +1155,17 @@ int sf_layer_forward(sf_ctx* c, void* stream, int layer, const void* x_in, void*
   if (!c || !x_in || !x_out) { set_error("sf_layer_forward: null argument"); return SF_ERR_INVALID; }
   if (!c->bound) { set_error("weights not bound"); return SF_ERR_STATE; }
   if (layer < 0 || layer >= c->L) { set_error("sf_layer_forward: layer %d out of range", layer); return SF_ERR_INVALID; }
+  if (B <= 0 || T <= 0 || S <= 0) { set_error("sf_layer_forward: bad shape B=%d T=%d S=%d", B, T, S); return SF_ERR_INVALID; }
+  DeviceGuard dg(c->device);
+  SF_CHECK(check_groups(c, false, layer, layer + 1, false, false));
+  if (kv) {
+    // block-level streaming: every layer of a step appends at the same position kv->seen; the caller
+    // advances the cache ONCE after the last layer with sf_kv_advance (the twin's DynamicCache grows per
+    // layer instead, …timesformer_encoder.py:517-518)
+    if (kv->ctx != c) { set_error("sf_layer_forward: the cache belongs to another context"); return SF_ERR_INVALID; }
+    if (kv->B != B || kv->S != S) { set_error("KV cache was created for B=%d S=%d, got B=%d S=%d", kv->B, kv->S, B, S); return SF_ERR_INVALID; }
+    if (kv->seen + T > kv->cap) { set_error("KV cache overflow: %d cached + %d new frames > capacity %d", kv->seen, T, kv->cap); return SF_ERR_STATE; }
+  }
   Bump b;
   b.base = static_cast<uint8_t*>(workspace); b.size = workspace_bytes;
   WsPlan w;
@@ -1069,9 +1178,49 @@ int sf_layer_forward(sf_ctx* c, void* stream, int layer, const void* x_in, void*
   return run_layer(c, st, layer, x_in, x_out, B, T, S, kv, attn_probs, w, w.stats[2], 1, w.stats[2]);
 }
 
+int sf_encoder_forward(sf_ctx* c, void* stream, const void* x_in, int B, int T, int S, sf_kv* kv, void* x_out,
+                       void* const* hidden_states, void* const* attentions, void* workspace, size_t workspace_bytes) {
+  if (!c || !x_in || (!x_out && !hidden_states)) { set_error("sf_encoder_forward: null argument"); return SF_ERR_INVALID; }
+  if (!c->bound) { set_error("weights not bound"); return SF_ERR_STATE; }
+  if (B <= 0 || T <= 0 || S <= 0) { set_error("sf_encoder_forward: bad shape B=%d T=%d S=%d", B, T, S); return SF_ERR_INVALID; }
+  DeviceGuard dg(c->device);
+  SF_CHECK(check_groups(c, false, 0, c->L, false, false));
+  if (kv) {
+    if (kv->ctx != c) { set_error("sf_encoder_forward: the cache belongs to another context"); return SF_ERR_INVALID; }
+    if (kv->B != B || kv->S != S) { set_error("KV cache was created for B=%d S=%d, got B=%d S=%d", kv->B, kv->S, B, S); return SF_ERR_INVALID; }
+    if (kv->seen + T > kv->cap) { set_error("KV cache overflow: %d cached + %d new frames > capacity %d", kv->seen, T, kv->cap); return SF_ERR_STATE; }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Bump b;
+  b.base = static_cast<uint8_t*>(workspace); b.size = workspace_bytes;
+  WsPlan w;
+  const long M = static_cast<long>(B) * T * S;
+  void* x = hidden_states ? nullptr : b.take(static_cast<size_t>(M) * c->D * 2);
+  SF_CHECK(carve_layer_ws(c, M, b, w));
+  // the rows come from the caller: one pass for their LayerNorm statistics, after that the statistics are
+  // by-products of the GEMM epilogues exactly as inside sf_forward
+  SF_CHECK(rowstats(st, c->cfg.dtype, x_in, c->D, static_cast<int>(M), c->D, w.stats[2]));
+  int parts = 1;
+  bool qkv_ready = false;
+  const void* cur = x_in;
+  for (int l = 0; l < c->L; ++l) {
+    void* nxt = hidden_states ? hidden_states[l + 1] : (l + 1 == c->L ? x_out : x);
+    const LayerW* next = (l + 1 < c->L && !phase_prof_enabled()) ? &c->layers[l + 1] : nullptr;
+    bool next_done = false;
+    SF_CHECK(run_layer(c, st, l, cur, nxt, B, T, S, kv, attentions ? static_cast<float*>(attentions[l]) : nullptr, w,
+                       w.stats[2], parts, w.stats[2], nullptr, qkv_ready, next, &next_done, &parts));
+    qkv_ready = next_done;
+    cur = nxt;
+  }
+  if (kv) { kv->seen += T; kv->seen_dirty = true; }
+  return 0;
+}
+
 int sf_final_norm(sf_ctx* c, void* stream, const void* x, int B, int T, int S, void* last_hidden) {
   if (!c || !x || !last_hidden) { set_error("sf_final_norm: null argument"); return SF_ERR_INVALID; }
   if (!c->bound) { set_error("weights not bound"); return SF_ERR_STATE; }
+  DeviceGuard dg(c->device);
+  SF_CHECK(check_groups(c, false, 0, 0, true, false));
   return layernorm(static_cast<cudaStream_t>(stream), c->cfg.dtype, x, c->D, c->post_g, c->post_b, c->cfg.layer_norm_eps,
                    last_hidden, c->D, static_cast<long>(B) * T * S, c->D, T > 1 ? kRowBNTtoBTN : kRowIdentity, T, S);
 }
@@ -1080,6 +1229,7 @@ int sf_head_forward(sf_ctx* c, void* stream, const void* tokens, int frames, int
                     size_t workspace_bytes) {
   if (!c || !tokens || !pooled) { set_error("sf_head_forward: null argument"); return SF_ERR_INVALID; }
   if (!c->bound) { set_error("weights not bound"); return SF_ERR_STATE; }
+  DeviceGuard dg(c->device);
   Bump b;
   b.base = static_cast<uint8_t*>(workspace); b.size = workspace_bytes;
   return run_head(c, static_cast<cudaStream_t>(stream), tokens, frames, S, pooled, b);
@@ -1106,7 +1256,8 @@ int sf_op_layernorm(void* stream, int dtype, const void* x, int ldx, const float
 }
 int sf_op_im2col(void* stream, int pix_dtype, const void* pixels, int act_dtype, void* out, int BT, int C, int Hh, int Ww,
                  int P) {
-  return im2col_patches(static_cast<cudaStream_t>(stream), pix_dtype, pixels, act_dtype, out, BT, C, Hh, Ww, P);
+  static const float half[4] = {0.5f, 0.5f, 0.5f, 0.5f};   // uint8 pixels: Normalize(0.5, 0.5)
+  return im2col_patches(static_cast<cudaStream_t>(stream), pix_dtype, pixels, act_dtype, out, BT, C, Hh, Ww, P, half, half);
 }
 int sf_op_temporal_attention(void* stream, int dtype, const void* qkv, int ld_qkv, const void* kcache, const void* vcache,
                              int Tcap, void* out, int ld_out, int sites, int heads, int Tq, int Tk, int q_off, int causal,

@@ -8,8 +8,9 @@
 
 namespace sf {
 
-enum DType : int { kBF16 = 0, kF16 = 1, kF32 = 2 };
-inline size_t dtype_size(int dt) { return dt == kF32 ? 4 : 2; }
+// kU8 / kU8HWC are PIXEL formats only: planar [.., C, H, W] and interleaved [.., H, W, C] uint8 frames
+enum DType : int { kBF16 = 0, kF16 = 1, kF32 = 2, kU8 = 3, kU8HWC = 4 };
+inline size_t dtype_size(int dt) { return dt == kF32 ? 4 : (dt == kU8 || dt == kU8HWC) ? 1 : 2; }
 
 enum RowMap : int {
   kRowIdentity = 0,
@@ -92,9 +93,11 @@ int layernorm(cudaStream_t stream, int dtype, const void* x, int ldx, const floa
               int S);
 
 // pixels [BT, C, H, W] (pix_dtype: bf16/f16/f32) -> patch-major A[(bt*S + n), C*P*P] in act dtype,
-// K ordered (c, kh, kw) like Conv2d.weight.reshape(D, -1).
+// K ordered (c, kh, kw) like Conv2d.weight.reshape(D, -1).  uint8 pixels (kU8: [BT, C, H, W], kU8HWC:
+// [BT, H, W, C], C <= 4) are normalised on the way: (x / 255 - mean[c]) / std[c], evaluated in fp32 in
+// exactly that order (ClipToTensor + Normalize of the reference's loaders), mean/std host arrays of 4.
 int im2col_patches(cudaStream_t stream, int pix_dtype, const void* pixels, int act_dtype, void* out,
-                   int BT, int C, int H, int W, int P);
+                   int BT, int C, int H, int W, int P, const float* mean = nullptr, const float* std = nullptr);
 
 // Temporal attention over frames, one (site, head) per warp task.
 //   q rows: qkv[(site*Tq + i), h*64 + d]                (row stride ld_qkv; q at col 0)

@@ -91,8 +91,13 @@ def sharded_forward(model, pixel_values_global: torch.Tensor, group: Optional["d
     Returns ``(local_output, pooler_output_global_or_None)``.  ``last_hidden_state`` stays local:
     only per-sample dense heads consume it.
     """
+    if forward_kwargs.get("return_dict") is False:
+        # the tuple form is (last_hidden_state[, hidden_states][, attentions]) — it has no pooled output
+        raise ValueError("sharded_forward needs return_dict=True: the tuple output carries no pooler_output")
     local = shard_clips(pixel_values_global, group)
     out = model(local, **forward_kwargs)
-    pooled = out.pooler_output if hasattr(out, "pooler_output") else out[1]
+    if not hasattr(out, "pooler_output") or out.pooler_output is None:
+        raise ValueError("the model returned no pooler_output to gather (return_dict=False in its config?)")
+    pooled = out.pooler_output
     gathered = gather_pooler_output(pooled, pixel_values_global.shape[0], group) if gather else None
     return out, gathered
