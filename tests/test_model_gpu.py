@@ -555,9 +555,9 @@ def test_standalone_submodules_in_a_foreign_model_ar_recipe():
     check("stand-alone encoder", enc.last_hidden_state, xs[-1], t["lhs"], t["cos"])
     seq = O.layer_norm(xs[-1], w["post_layernorm.weight"], w["post_layernorm.bias"], cfg.layer_norm_eps)
     pooled = O.pooling_head(w, cfg, seq.reshape(2 * 4, -1, 768)).reshape(2, 4, 768).mean(1)
-    fcw = clf.fc_norm.weight.float().cpu().numpy(), clf.fc_norm.bias.float().cpu().numpy()
-    want = O.linear(O.layer_norm(pooled, fcw[0], fcw[1], cfg.layer_norm_eps), clf.classifier.weight.float().cpu().numpy(),
-                    clf.classifier.bias.float().cpu().numpy())
+    npy = lambda t: t.detach().float().cpu().numpy()   # noqa: E731
+    want = O.linear(O.layer_norm(pooled, npy(clf.fc_norm.weight), npy(clf.fc_norm.bias), cfg.layer_norm_eps),
+                    npy(clf.classifier.weight), npy(clf.classifier.bias))
     check("AR logits", logits, want, 3e-2, 0.999)
     # each stand-alone module owns its engine and binds only its own parameter group
     assert len(clf.embeddings._sf_engines()) == 1 and len(clf.encoder._sf_engines()) == 1 and len(clf.head._sf_engines()) == 1
