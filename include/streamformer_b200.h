@@ -210,6 +210,10 @@ int sf_op_im2col(void* stream, int pix_dtype, const void* pixels, int act_dtype,
 int sf_op_temporal_attention(void* stream, int dtype, const void* qkv, int ld_qkv, const void* kcache,
                              const void* vcache, int Tcap, void* out, int ld_out, int sites, int heads,
                              int Tq, int Tk, int q_off, int causal, float scale);
+/* streaming decode: one new frame per site; kv_append + temporal attention over the cache in one kernel
+ * (cache capacity <= 96 frames; `seen` frames are cached before the call, the new row lands at index `seen`) */
+int sf_op_temporal_decode(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
+                          int Tcap, void* out, int ld_out, int sites, int heads, int seen, float scale);
 int sf_op_kv_append(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
                     int Tcap, int sites, int heads, int Tq, int pos0);
 /* T_inner <= 1: token n of frame f at row f*S + n; T_inner > 1: at row (b*S + n)*T_inner + t with

@@ -14,6 +14,8 @@
 
 #include <type_traits>
 
+#include <cuda.h>
+
 #include "sf_kernels.h"
 #include "sf_ptx.cuh"
 #include "sf_tma.h"
@@ -334,6 +336,151 @@ __global__ void __launch_bounds__(kTWarps * 32, 4) temporal_attn_fast_kernel(con
 }
 
 // K/V slices of the fresh QKV projection -> cache[site][head][pos0 + i][64]
+// Streaming decode: ONE new frame per site attending to its cached history (BASELINE configs[2]: B=4, one
+// frame per step; reference: the KV twin's cached attention, …timesformer_encoder.py:491-560).  A (site, head)
+// history is one contiguous block of rows in the cache, staged into shared memory as 16-row slabs by TMA
+// (cp.async.bulk.tensor, SWIZZLE_128B — the layout ldmatrix wants) completing on an mbarrier; every warp is
+// persistent and keeps a ring of up to 8 tasks in flight (the ring depth adapts to the history length, 48 KB of
+// staging per warp), and because the history does not depend on the QKV GEMM that precedes this kernel in the
+// stream, the first ring fill is issued BEFORE griddepcontrol.wait and overlaps that GEMM's tail.  The new
+// frame's key/value row comes straight from the QKV buffer, is dropped into the staged tile and appended to the
+// cache by the same warp (kv_append fused); the arithmetic is the generic kernel's (mma.sync m16n8k16 over
+// 16-key slabs with online softmax; one valid query row per tile — the work is ~0.03 GFLOP per launch).
+// The per-task dependent chain (ldmatrix -> mma -> softmax -> mma) is latency-bound, so the CTA carries as
+// many warps as the staging budget allows: 192 KB of rings split over 12 warps (caches of up to 64 frames: a
+// whole history fits one 16 KB stage) or 8 warps (up to 96 frames); the next task's query / new-row words are
+// fetched while the current task is computed.
+constexpr int kDecStaging = 192 * 1024;
+constexpr int kDecMaxStages = 8;
+constexpr int kDecSlabBytes = 16 * 128;             // 16 rows x 64 two-byte elements
+constexpr int kDecMaxRows = 96;                     // frames incl. the new one
+constexpr int kDecMaxWarps = 12;
+constexpr int kDecSmem = kDecStaging + kDecMaxWarps * kDecMaxStages * 8 + 1024;
+inline int dec_warps(int Tcap) { return Tcap <= 64 ? 12 : 8; }
+
+template <typename T>
+__global__ void __launch_bounds__(kDecMaxWarps * 32, 1)
+temporal_decode_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                       const TemporalArgs a, T* __restrict__ kc, T* __restrict__ vc, int Tcap) {
+  const int kDecWarps = blockDim.x >> 5;
+  const int kDecRing = kDecStaging / kDecWarps;      // staging bytes per warp (16 KB or 24 KB)
+  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+  extern __shared__ uint8_t dsm_raw[];
+  uint8_t* dsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  uint8_t* ring = dsm + warp * kDecRing;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + kDecStaging) + warp * kDecMaxStages;
+  if (lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int s = 0; s < kDecMaxStages; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  // rows of a slab that no load covers must hold finite values (their probabilities are exactly 0)
+  for (int i = lane; i < kDecRing / 16; i += 32) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  __syncwarp();
+  // frames cached before this step (device counter under a captured graph: written by the PREVIOUS step's graph)
+  const int seen = a.seen_dev ? *a.seen_dev : a.q_off;
+  const long nwarps = static_cast<long>(gridDim.x) * kDecWarps;
+  const long task0 = static_cast<long>(blockIdx.x) * kDecWarps + warp;
+  const int slabs = (seen + 1 + 15) >> 4;            // slabs of the staged tile incl. the new row
+  const int loaded = (seen + 15) >> 4;               // slabs that come from the cache
+  const uint32_t region = static_cast<uint32_t>(slabs) * kDecSlabBytes;   // bytes of the K (or V) part of a stage
+  int nst = kDecRing / static_cast<int>(2 * region);   // >= 1: the host picks the warp count from the cache capacity
+  if (nst > kDecMaxStages) nst = kDecMaxStages;
+  auto issue = [&](long task, int s) {
+    if (loaded == 0) return;
+    uint8_t* base = ring + static_cast<size_t>(s) * 2 * region;
+    mbar_arrive_expect_tx(&bars[s], 2u * loaded * kDecSlabBytes);
+    const int row0 = static_cast<int>(task * Tcap);
+    for (int i = 0; i < loaded; ++i) {
+      tma_load_2d(base + i * kDecSlabBytes, &tmK, &bars[s], 0, row0 + 16 * i);
+      tma_load_2d(base + region + i * kDecSlabBytes, &tmV, &bars[s], 0, row0 + 16 * i);
+    }
+  };
+  if (lane == 0) {
+    for (int s = 0; s < nst; ++s) {
+      const long t = task0 + s * nwarps;
+      if (t < a.tasks) issue(t, s);
+    }
+  }
+  griddep_wait();               // from here on: q / k_new / v_new written by the QKV GEMM
+  griddep_launch_dependents();
+
+  const int D = a.heads * kHd;
+  const long task_stride = static_cast<long>(Tcap) * kHd;           // elements between (site, head) blocks
+  int s = 0;
+  uint32_t phase = 0;
+  // the (site, head) row words of a task: query fragments (one valid query row: tile row 0), new key / value pair
+  auto row_of = [&](long task) {
+    const long site = task / a.heads;
+    const int h = static_cast<int>(task - site * a.heads);
+    return reinterpret_cast<const T*>(a.q) + site * a.q_ld + h * kHd;
+  };
+  uint32_t qa_n[4][4], k2_n = 0u, v2_n = 0u;
+  if (task0 < a.tasks) {
+    const T* row = row_of(task0);
+    k2_n = *reinterpret_cast<const uint32_t*>(row + D + 2 * lane);
+    v2_n = *reinterpret_cast<const uint32_t*>(row + 2 * D + 2 * lane);
+    load_q_frags<T>(qa_n, row, row, g == 0, false, c);
+  }
+  for (long task = task0; task < a.tasks; task += nwarps) {
+    const long site = task / a.heads;
+    const int h = static_cast<int>(task - site * a.heads);
+    const uint32_t k2 = k2_n, v2 = v2_n;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { qa[i][0] = qa_n[i][0]; qa[i][1] = qa_n[i][1]; qa[i][2] = qa_n[i][2]; qa[i][3] = qa_n[i][3]; }
+    if (task + nwarps < a.tasks) {          // next task's words travel while this one is computed
+      const T* row = row_of(task + nwarps);
+      k2_n = *reinterpret_cast<const uint32_t*>(row + D + 2 * lane);
+      v2_n = *reinterpret_cast<const uint32_t*>(row + 2 * D + 2 * lane);
+      load_q_frags<T>(qa_n, row, row, g == 0, false, c);
+    }
+    // fused kv_append: cache[site][head][seen][:] = new row
+    *reinterpret_cast<uint32_t*>(kc + task * task_stride + static_cast<long>(seen) * kHd + 2 * lane) = k2;
+    *reinterpret_cast<uint32_t*>(vc + task * task_stride + static_cast<long>(seen) * kHd + 2 * lane) = v2;
+    uint8_t* Ks = ring + static_cast<size_t>(s) * 2 * region;
+    uint8_t* Vs = Ks + region;
+    if (loaded) mbar_wait(&bars[s], phase);
+    // the new row joins the staged tile at row `seen` (lane covers 4 bytes of chunk lane/4)
+    *reinterpret_cast<uint32_t*>(Ks + tile_off(seen, lane >> 2) + (lane & 3) * 4) = k2;
+    *reinterpret_cast<uint32_t*>(Vs + tile_off(seen, lane >> 2) + (lane & 3) * 4) = v2;
+    __syncwarp();
+    const uint32_t ks_u = smem_u32(Ks), vs_u = smem_u32(Vs);
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
+    for (int kb0 = 0; kb0 <= seen; kb0 += 16) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      qk_16keys<kBf16>(s0, s1, qa, ks_u, kb0, lane);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j0 = kb0 + 2 * c + e, j1 = kb0 + 8 + 2 * c + e;
+        s0[e] = j0 <= seen ? s0[e] * a.scale_log2 : -INFINITY;
+        s0[2 + e] = j0 <= seen ? s0[2 + e] * a.scale_log2 : -INFINITY;
+        s1[e] = j1 <= seen ? s1[e] * a.scale_log2 : -INFINITY;
+        s1[2 + e] = j1 <= seen ? s1[2 + e] * a.scale_log2 : -INFINITY;
+      }
+      uint32_t pa[4];
+      softmax_step<T>(s0, s1, m_run, l_run, o, pa);
+      pv_16keys<kBf16>(o, pa, vs_u, kb0, lane);
+    }
+    T* orow = reinterpret_cast<T*>(a.out) + site * a.out_ld + h * kHd;
+    finalize_store<T>(o, l_run, orow, orow, g == 0, false, c);
+    __syncwarp();                 // every lane is done with this stage before it is refilled
+    const long nxt = task + static_cast<long>(nst) * nwarps;
+    if (lane == 0 && nxt < a.tasks) {
+      fence_proxy_async_smem();   // the generic-proxy stores of the new row precede the async-proxy refill
+      issue(nxt, s);
+    }
+    if (++s == nst) { s = 0; phase ^= 1; }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 kv_append_kernel(const T* __restrict__ qkv, long ld, T* __restrict__ kc, T* __restrict__ vc, int Tcap,
@@ -805,6 +952,69 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
   if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, temporal_attn_kernel<__nv_bfloat16>, a);
   else cudaLaunchKernelEx(&lc.cfg, temporal_attn_kernel<__half>, a);
   return check_launch("temporal_attention");
+}
+
+bool temporal_decode_supported(int Tcap, int Tq) {
+  static const bool on = [] { const char* e = getenv("SF_TEMPORAL_DECODE"); return !(e && e[0] == '0'); }();
+  return on && Tq == 1 && Tcap <= kDecMaxRows && Tcap >= 1;
+}
+
+// 2-D map over a cache tensor viewed as [sites*heads*Tcap rows][64]: 16-row boxes, SWIZZLE_128B
+int make_cache_map(CUtensorMap* map, int dtype, const void* base, long rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -3;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kHd), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kHd) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kHd), 16u};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(cache map) failed (%d): rows=%ld base=%p", (int)r, rows, base); return -3; }
+  return 0;
+}
+
+int temporal_decode(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache, int Tcap,
+                    void* out, int ld_out, int sites, int heads, int seen, float scale, const int* seen_dev) {
+  if (sites <= 0) return 0;
+  if (dtype != kBF16 && dtype != kF16) { set_error("temporal_decode: dtype must be bf16/f16"); return -1; }
+  if (!temporal_decode_supported(Tcap, 1)) { set_error("temporal_decode: cache capacity %d exceeds %d frames", Tcap, kDecMaxRows); return -1; }
+  if (static_cast<long>(sites) * heads * Tcap > 0x7fffffffL) { set_error("temporal_decode: cache too large for 32-bit row coordinates"); return -1; }
+  if (seen + 1 > Tcap) { set_error("temporal_decode: %d + 1 frames exceed cache capacity %d", seen, Tcap); return -1; }
+  if ((ld_qkv % 2) || (ld_out % 2)) { set_error("temporal_decode: bad leading dims"); return -1; }
+  TemporalArgs a;
+  a.q = qkv; a.q_ld = ld_qkv;
+  a.k = kcache; a.v = vcache;
+  a.kv_site_stride = static_cast<long>(heads) * Tcap * kHd;
+  a.kv_head_stride = static_cast<long>(Tcap) * kHd;
+  a.kv_row_stride = kHd;
+  a.out = out; a.out_ld = ld_out;
+  a.sites = sites; a.heads = heads; a.Tq = 1; a.Tk = seen + 1; a.q_off = seen; a.causal = 1; a.qtiles = 1;
+  a.tasks = static_cast<long>(sites) * heads;
+  a.scale_log2 = scale * kLog2e;
+  a.seen_dev = seen_dev;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(temporal_decode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmem);
+    cudaFuncSetAttribute(temporal_decode_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmem);
+    attr_set = true;
+  }
+  const int kDecWarps = dec_warps(Tcap);
+  long blocks = (a.tasks + kDecWarps - 1) / kDecWarps;
+  if (blocks > num_sms()) blocks = num_sms();
+  ProfScope ps(stream, kProfTemporalAttn, 4.0 * sites * heads * static_cast<double>(seen + 1) * kHd,
+               2.0 * sites * heads * kHd * (5.0 + 2.0 * seen));
+  CUtensorMap tmK, tmV;
+  int rc = make_cache_map(&tmK, dtype, kcache, static_cast<long>(sites) * heads * Tcap);
+  if (rc) return rc;
+  rc = make_cache_map(&tmV, dtype, vcache, static_cast<long>(sites) * heads * Tcap);
+  if (rc) return rc;
+  LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(kDecWarps * 32), kDecSmem, stream);
+  if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, temporal_decode_kernel<__nv_bfloat16>, tmK, tmV, a, reinterpret_cast<__nv_bfloat16*>(kcache),
+                                         reinterpret_cast<__nv_bfloat16*>(vcache), Tcap);
+  else cudaLaunchKernelEx(&lc.cfg, temporal_decode_kernel<__half>, tmK, tmV, a, reinterpret_cast<__half*>(kcache),
+                          reinterpret_cast<__half*>(vcache), Tcap);
+  return check_launch("temporal_decode");
 }
 
 int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,

@@ -336,7 +336,9 @@ int run_layer(sf_ctx* c, cudaStream_t st, int l, const void* x_in, void* x_out, 
   if (!qkv_ready)
     SF_CHECK(gemm(st, dt, x_in, D, lw.t_qkv_w, D, w.qkv, 3 * D, M, 3 * D, D,
                   epi_ln(lw.t_qkv_b, lw.t_qkv_cs, st_in, parts_in, eps)));
-  if (kv) {
+  if (kv && temporal_decode_supported(kv->cap, T)) {
+    SF_CHECK(temporal_decode(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, w.ctx, D, B * S, H, kv->seen, scale, seen_dev));
+  } else if (kv) {
     SF_CHECK(kv_append(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, B * S, H, T, kv->seen, seen_dev));
     SF_CHECK(temporal_attention(st, dt, w.qkv, 3 * D, kv->k(l), kv->v(l), kv->cap, w.ctx, D, B * S, H, T,
                                 kv->seen + T, kv->seen, c->cfg.causal_temporal, scale, seen_dev));
@@ -1074,6 +1076,8 @@ int sf_kv_create(sf_ctx* c, int B, int S, int max_frames, int time_horizon, sf_k
   kv->kv_bytes = static_cast<size_t>(B) * S * c->H * max_frames * 64 * 2;
   kv->layer_stride = 2 * kv->kv_bytes;
   cudaError_t e = cudaMalloc(&kv->mem, kv->layer_stride * c->L);
+  // rows past the stream position are read as part of 16-row slabs (their probabilities are exactly 0): they must be finite
+  if (e == cudaSuccess) e = cudaMemset(kv->mem, 0, kv->layer_stride * c->L);
   if (e == cudaSuccess) e = cudaMalloc(&kv->d_seen, sizeof(int));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&kv->cap_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
@@ -1264,6 +1268,11 @@ int sf_op_temporal_attention(void* stream, int dtype, const void* qkv, int ld_qk
                              float scale) {
   return temporal_attention(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, kcache, vcache, Tcap, out, ld_out, sites,
                             heads, Tq, Tk, q_off, causal, scale);
+}
+int sf_op_temporal_decode(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache, int Tcap,
+                          void* out, int ld_out, int sites, int heads, int seen, float scale) {
+  return temporal_decode(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, kcache, vcache, Tcap, out, ld_out, sites,
+                         heads, seen, scale);
 }
 int sf_op_kv_append(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache, int Tcap, int sites,
                     int heads, int Tq, int pos0) {

@@ -112,6 +112,12 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
                        const void* vcache, int Tcap, void* out, int ld_out, int sites, int heads,
                        int Tq, int Tk, int q_off, int causal, float scale, const int* seen_dev = nullptr);
 
+// Streaming decode (Tq == 1 with a cache): kv_append + temporal_attention in one kernel, the (site, head)
+// histories staged by cp.async.bulk (attention.cu).  Supported for caches of up to 96 frames.
+bool temporal_decode_supported(int Tcap, int Tq);
+int temporal_decode(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache, int Tcap,
+                    void* out, int ld_out, int sites, int heads, int seen, float scale, const int* seen_dev = nullptr);
+
 // Append the K and V slices of qkv (rows (site*Tq + i)) into cache[site][head][pos0 + i][64].
 int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,
               int Tcap, int sites, int heads, int Tq, int pos0, const int* seen_dev = nullptr);

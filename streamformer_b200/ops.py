@@ -101,6 +101,17 @@ def temporal_attention(qkv: torch.Tensor, sites: int, heads: int, Tq: int, causa
     return out
 
 
+def temporal_decode(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, sites: int, heads: int, seen: int,
+                    scale: float) -> torch.Tensor:
+    """One new frame per site: appends its K/V row at cache index ``seen`` and attends to rows 0..seen."""
+    _req(qkv, kcache, vcache)
+    out = torch.empty(sites, heads * 64, dtype=qkv.dtype, device=qkv.device)
+    N.check(N.load().sf_op_temporal_decode(_stream(), sf_dtype(qkv.dtype), qkv.data_ptr(), qkv.stride(0), kcache.data_ptr(),
+                                           vcache.data_ptr(), kcache.shape[2], out.data_ptr(), out.stride(0), sites, heads,
+                                           seen, scale), "sf_op_temporal_decode")
+    return out
+
+
 def kv_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, sites: int, heads: int, Tq: int,
               pos0: int) -> None:
     _req(qkv, kcache, vcache)

@@ -302,6 +302,32 @@ def test_temporal_attention_kv_cache(Tnew, steps):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("sites,cap,steps", [(784, 64, 64), (61, 96, 96), (5, 8, 8), (3, 33, 33)])
+def test_temporal_decode_kernel(dtype, sites, cap, steps):
+    """Streaming decode kernel (bulk-copy staged histories, fused append): every step equals the matching row of
+    the one-shot causal attention; the cache it leaves behind equals what kv_append writes; ring depths 8 -> 2."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(17)
+    H, D = 12, 768
+    qkv_all = torch.randn(sites, steps, 3 * D, generator=g).to(DEV, dtype)
+    x = qkv_all.float().view(sites, steps, 3, H, 64).permute(2, 0, 3, 1, 4)
+    mask = torch.tril(torch.ones(steps, steps, dtype=torch.bool, device=DEV))
+    ref_all = _attn_ref(x[0], x[1], x[2], 0.125, mask).transpose(1, 2).reshape(sites, steps, D)
+    kc = torch.zeros(sites, H, cap, 64, device=DEV, dtype=dtype)
+    vc = torch.zeros_like(kc)
+    kc2, vc2 = torch.zeros_like(kc), torch.zeros_like(kc)
+    for s in range(steps):
+        step = qkv_all[:, s].contiguous()
+        out = ops.temporal_decode(step, kc, vc, sites, H, s, 0.125)
+        _close(out, ref_all[:, s], dtype, f"decode step {s}", scale=2.0)
+        if s in (0, 1, steps // 2, steps - 1):
+            ops.kv_append(step, kc2, vc2, sites, H, 1, s)
+            assert torch.equal(kc[:, :, s], kc2[:, :, s]) and torch.equal(vc[:, :, s], vc2[:, :, s])
+    with pytest.raises(Exception, match="capacity"):
+        ops.temporal_decode(qkv_all[:, 0].contiguous(), kc, vc, sites, H, cap, 0.125)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("frames,S", [(16, 196), (3, 49), (2, 392), (1, 64), (2, 1)])
 def test_spatial_attention(dtype, frames, S):
     ops = _ops()
