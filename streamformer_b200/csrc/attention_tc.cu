@@ -53,6 +53,29 @@ template <typename T> struct Fmt;
 template <> struct Fmt<__half> { static constexpr int value = 0; };
 template <> struct Fmt<__nv_bfloat16> { static constexpr int value = 1; };
 
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x) taken from the low mantissa
+// bits of x + 1.5 * 2^23, 2^f by a cubic on [-0.5, 0.5] (max relative error 1.9e-4, an order of magnitude
+// below the rounding of P to a 16-bit operand), 2^n added into the exponent field.  x is clamped at -120
+// (2^-120 is 0 for every purpose here) so the exponent arithmetic cannot wrap.
+// Measured on B200 (round 2, cfg2 shapes, tools/exp_poly.sh): 0 of 4 -> 60.4 us, 1 of 4 -> 60.8, 2 of 4 -> 63.4,
+// 3 of 4 -> 67.9: the exponential pass is NOT MUFU-bound (it waits on the tcgen05.ld / tcgen05.st round trips of
+// its 16-column chunks), so the offload stays off; kept as a compile-time experiment (-DSF_EXP2_POLY_PER4=n).
+#ifndef SF_EXP2_POLY_PER4
+#define SF_EXP2_POLY_PER4 0
+#endif
+constexpr int kExp2PolyPer4 = SF_EXP2_POLY_PER4;     // of every 4 consecutive elements, how many use exp2_fma
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -120.0f);
+  const float magic = 12582912.0f;                    // 1.5 * 2^23
+  const float t = x + magic;
+  const float f = x - (t - magic);
+  float p = 0.05587553605437279f;
+  p = fmaf(p, f, 0.24229462444782257f);
+  p = fmaf(p, f, 0.6931272745132446f);
+  p = fmaf(p, f, 0.999948263168335f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(384, 1)
 spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
@@ -211,9 +234,16 @@ spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 float pj[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  float e;
-                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(v[hh][j]), a.scale_log2, nm)));
-                  pj[j] = e;
+                  const float x = fmaf(__uint_as_float(v[hh][j]), a.scale_log2, nm);
+                  // the exponential pass is bound by the MUFU pipe (16 ex2 per clock and SM): kExp2Poly of every
+                  // 16 elements take the FMA pipe instead (exp2_fma below), the rest MUFU.EX2
+                  if ((j % 4) < kExp2PolyPer4) {
+                    pj[j] = exp2_fma(x);
+                  } else {
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+                    pj[j] = e;
+                  }
                 }
                 if (cc >= nfull) {
 #pragma unroll
