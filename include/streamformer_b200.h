@@ -232,6 +232,25 @@ int sf_op_pool_attention(void* stream, int dtype, const void* kv, int ld_kv, con
 int sf_op_pool_probe(void* stream, int dtype, const void* tokens, int ld, const float* u, const void* wv,
                      const float* bv, void* out, int ld_out, int frames, int heads, int S);
 
+/* ---- task head on the gathered pooler_output (the step after the path) -------- */
+/* replaces TimesformerVideoClassificationHead.forward (…siglip.py:1704-1726: image = pooler_output[:, -1],
+ * L2-normalised; logits_per_image = exp(logit_scale) * image . text^T + logit_bias; loss =
+ * -logsigmoid(target_labels * logits).sum() / B) and SigLipLoss._loss / the retrieval head (…siglip.py:220-243,
+ * 2324-2351; both sides normalised, labels 2*eye - 1; with image rows = this rank's clips and text rows = every
+ * rank's captions, diag_offset = rank * B_local reproduces the reference's ring exchange of negatives).
+ *   image [B, D] / text [L, D] in `dtype` (row strides ld_i / ld_t elements), logit_scale (pre-exp) and
+ *   logit_bias device scalars; targets int64 [B] or NULL (then +1 sits at column i + diag_offset; < 0: none);
+ *   logits fp32 [B, L] or NULL; *loss += result (zero it first); dlogits [B, L] in `dtype` or NULL receives
+ *   d loss / d logits, dparams NULL or float[2] += (d loss / d logit_scale, d loss / d logit_bias). */
+int sf_op_siglip_head(void* stream, int dtype, const void* image, int ld_i, const void* text, int ld_t, int B,
+                      int L, int D, const float* logit_scale, const float* logit_bias, int normalize_image,
+                      int normalize_text, const int64_t* targets, int diag_offset, float loss_div, float* logits,
+                      int ld_logits, float* loss, void* dlogits, int ld_dlogits, float* dparams);
+
+/* backward of the head's image normalisation: dx = (g - x^ (x^ . g)) / |x|, g = exp(*gscale) * dxhat */
+int sf_op_l2norm_backward(void* stream, int dtype, const void* x, int ldx, const void* dxhat, int ldg,
+                          const float* gscale, void* dx, int ldo, int B, int D);
+
 #ifdef __cplusplus
 }
 #endif

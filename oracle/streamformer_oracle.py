@@ -430,3 +430,49 @@ def flops_per_clip(cfg: OracleConfig, T: int) -> float:
     per_layer += 2 * 2 * M * D * I             # MLP
     head = 2 * M * D * 2 * D + 2 * 2 * T * N * D + 2 * T * D * D + 2 * 2 * T * D * I
     return float(2 * M * Kp * D + L * per_layer + head)
+
+
+# --------------------------------------------------------------------------------------- task heads
+def log_sigmoid(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.float64)
+    return np.minimum(x, 0.0) - np.log1p(np.exp(-np.abs(x)))
+
+
+def classification_head(pooler_output: np.ndarray, label_embeddings: np.ndarray, logit_scale: float, logit_bias: float,
+                        labels: np.ndarray) -> Tuple[float, np.ndarray]:
+    """TimesformerVideoClassificationHead.forward (R:1704-1726): last-frame pooled feature, L2-normalised; the label
+    embeddings are used as stored (already normalised / averaged, R:1665-1672).
+    Returns (loss, logits_per_image [B, L])."""
+    img = pooler_output[:, -1, :].astype(np.float64)
+    img = img / np.linalg.norm(img, axis=-1, keepdims=True)                         # R:1711
+    logits_per_text = label_embeddings.astype(np.float64) @ img.T * math.exp(logit_scale) + logit_bias   # R:1714-1718
+    logits = logits_per_text.T
+    target = -np.ones_like(logits)                                                  # R:1721-1724
+    target[np.arange(labels.shape[0]), labels] = 1.0
+    loss = -log_sigmoid(target * logits).sum() / labels.shape[0]                    # R:1725
+    return float(loss), logits.astype(F32)
+
+
+def siglip_loss(image_features: np.ndarray, text_features: np.ndarray, logit_scale_exp: float, logit_bias: float,
+                negative_only: bool = False) -> float:
+    """SigLipLoss._loss (R:220-243): features arrive normalised, logit_scale already exponentiated (R:2341-2343)."""
+    logits = logit_scale_exp * image_features.astype(np.float64) @ text_features.astype(np.float64).T + logit_bias
+    n = image_features.shape[0]
+    labels = -np.ones((n, text_features.shape[0]))
+    if not negative_only:
+        labels = labels + 2.0 * np.eye(n, text_features.shape[0])
+    return float(-log_sigmoid(labels * logits).sum() / n)
+
+
+def siglip_loss_world(image_features: List[np.ndarray], text_features: List[np.ndarray], logit_scale_exp: float,
+                      logit_bias: float) -> List[float]:
+    """SigLipLoss.forward with world_size = len(image_features) (R:245-297): rank r's loss is its own block plus a
+    negatives-only term against every other rank's text features (what the ring exchange accumulates)."""
+    out = []
+    for r, img in enumerate(image_features):
+        loss = siglip_loss(img, text_features[r], logit_scale_exp, logit_bias)
+        for q, txt in enumerate(text_features):
+            if q != r:
+                loss += siglip_loss(img, txt, logit_scale_exp, logit_bias, negative_only=True)
+        out.append(loss)
+    return out

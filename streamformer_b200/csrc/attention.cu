@@ -893,6 +893,158 @@ pool_probe_kernel(const T* __restrict__ x, long ld, const float* __restrict__ u,
   orow[lane + 32] = static_cast<T>(r1 + __ldg(bv + warp * kHd + lane + 32));
 }
 
+// ------------------------------------------------------------------------------- SigLIP task head
+// The step right after the encoder: the zero-shot classification head and the SigLIP sigmoid loss
+// on the (all-gathered) last-frame pooler_output (reference models/modeling_timesformer_siglip.py:1704-1726 and
+// 244-295, 2324-2351), as ONE launch: L2 normalisation of the image rows (and optionally of the text rows) folded
+// into the epilogue as fp32 row / column scales, logits = exp(logit_scale) * <x^, t^> + logit_bias on the tensor
+// cores (mma.sync m16n8k16, fp32 accumulate), -logsigmoid(label * logit) summed into a device scalar, and — for
+// training — d loss / d logits in the same pass.  Labels: +1 at column targets[i] (classification) or at column
+// i + diag_offset (contrastive; diag_offset < 0: negatives only, the reference's ring-exchange terms), -1 elsewhere.
+struct HeadArgs {
+  const void* image; long ld_i;        // [B, D]
+  const void* text; long ld_t;         // [L, D]
+  int B, L, D;
+  const float* logit_scale;            // device scalar, pre-exp
+  const float* logit_bias;             // device scalar or nullptr
+  int norm_image, norm_text;
+  const long long* targets;            // [B] or nullptr
+  int diag_offset;
+  float loss_scale;                    // 1 / batch divisor
+  float* logits; long ld_l;            // [B, L] fp32 or nullptr
+  float* loss;                         // += sum of -logsigmoid(label * logit) * loss_scale
+  void* dlogits; long ld_d;            // [B, L] activation dtype or nullptr: d loss / d logit
+  float* dparams;                      // nullptr or [2]: += d loss / d logit_scale, d loss / d logit_bias
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) siglip_head_kernel(const HeadArgs a) {
+  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+  __shared__ __align__(1024) uint8_t a_tile[16 * 128];
+  __shared__ __align__(1024) uint8_t b_tile[128 * 128];
+  __shared__ float inv_a[16], inv_b[128], red[3][4];
+  griddep_wait();
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int m0 = blockIdx.x * 16, n0 = blockIdx.y * 128;
+  const T* img = reinterpret_cast<const T*>(a.image);
+  const T* txt = reinterpret_cast<const T*>(a.text);
+  // fp32 row norms (one warp per row)
+  for (int r = warp; r < 16 + 128; r += 4) {
+    const bool is_a = r < 16;
+    const int row = is_a ? m0 + r : n0 + (r - 16);
+    const bool valid = is_a ? row < a.B : row < a.L;
+    const bool want = is_a ? a.norm_image != 0 : a.norm_text != 0;
+    float ss = 0.f;
+    if (valid && want) {
+      const T* p = is_a ? img + static_cast<long>(row) * a.ld_i : txt + static_cast<long>(row) * a.ld_t;
+      for (int d = lane; d < a.D; d += 32) { const float v = static_cast<float>(p[d]); ss = fmaf(v, v, ss); }
+      ss = warp_sum(ss);
+    }
+    if (lane == 0) {
+      const float inv = (valid && want) ? rsqrtf(ss) : 1.0f;
+      if (is_a) inv_a[r] = inv; else inv_b[r - 16] = inv;
+    }
+  }
+  float acc[2][2][4];     // [16-column group][n-tile][fragment]
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+  for (int k0 = 0; k0 < a.D; k0 += 64) {
+    __syncthreads();
+    {   // A: 16 rows x 8 chunks = one 16-byte chunk per thread; B: 128 rows x 8 chunks = 8 per thread
+      const int row = threadIdx.x >> 3, ch = threadIdx.x & 7;
+      const bool ok = (m0 + row) < a.B && (k0 + ch * 8) < a.D;
+      cp_async_16(a_tile + tile_off(row, ch), img + static_cast<long>(ok ? m0 + row : 0) * a.ld_i + (ok ? k0 + ch * 8 : 0), ok);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = threadIdx.x + 128 * i;
+        const int brow = idx >> 3, bch = idx & 7;
+        const bool okb = (n0 + brow) < a.L && (k0 + bch * 8) < a.D;
+        cp_async_16(b_tile + tile_off(brow, bch), txt + static_cast<long>(okb ? n0 + brow : 0) * a.ld_t + (okb ? k0 + bch * 8 : 0), okb);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qa[ks], smem_u32(a_tile) + tile_off(lane & 15, 2 * ks + (lane >> 4)));
+    qk_16keys<kBf16>(acc[0][0], acc[0][1], qa, smem_u32(b_tile), warp * 32, lane);
+    qk_16keys<kBf16>(acc[1][0], acc[1][1], qa, smem_u32(b_tile), warp * 32 + 16, lane);
+  }
+  const float scale = expf(*a.logit_scale);
+  const float bias = a.logit_bias ? *a.logit_bias : 0.f;
+  float loss = 0.f, dscale = 0.f, dbias = 0.f;
+#pragma unroll
+  for (int grp = 0; grp < 2; ++grp)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = (e < 2) ? g : g + 8;
+        const int col_in = warp * 32 + grp * 16 + nt * 8 + 2 * c + (e & 1);
+        const int row = m0 + r, col = n0 + col_in;
+        if (row < a.B && col < a.L) {
+          const float dot = acc[grp][nt][e] * inv_a[r] * inv_b[col_in];
+          const float z = fmaf(scale, dot, bias);
+          if (a.logits) a.logits[static_cast<long>(row) * a.ld_l + col] = z;
+          float label = -1.f;
+          if (a.targets) { if (a.targets[row] == col) label = 1.f; }
+          else if (a.diag_offset >= 0 && col == row + a.diag_offset) label = 1.f;
+          const float y = label * z;
+          // -logsigmoid(y) = max(-y, 0) + log1p(exp(-|y|))
+          loss += fmaxf(-y, 0.f) + log1pf(expf(-fabsf(y)));
+          if (a.dlogits) {
+            const float dz = -label / (1.0f + expf(y)) * a.loss_scale;      // d(-logsigmoid(y))/dz = -label * sigmoid(-y)
+            reinterpret_cast<T*>(a.dlogits)[static_cast<long>(row) * a.ld_d + col] = static_cast<T>(dz);
+            dscale = fmaf(dz, z - bias, dscale);     // d z / d logit_scale = exp(logit_scale) * dot = z - bias
+            dbias += dz;
+          }
+        }
+      }
+  loss = warp_sum(loss); dscale = warp_sum(dscale); dbias = warp_sum(dbias);
+  if (lane == 0) { red[0][warp] = loss; red[1][warp] = dscale; red[2][warp] = dbias; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(a.loss, (red[0][0] + red[0][1] + red[0][2] + red[0][3]) * a.loss_scale);
+    if (a.dparams) {
+      atomicAdd(a.dparams, red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+      atomicAdd(a.dparams + 1, red[2][0] + red[2][1] + red[2][2] + red[2][3]);
+    }
+  }
+}
+
+// Backward of the row-wise L2 normalisation x^ = x / |x| feeding the head above:
+//   dx = (g - x^ (x^ . g)) / |x|,  g = gscale * dxhat  (gscale = exp(logit_scale), a device scalar or nullptr)
+template <typename T>
+__global__ void __launch_bounds__(128) l2norm_bwd_kernel(const T* __restrict__ x, long ldx, const T* __restrict__ dxhat, long ldg,
+                                                         const float* __restrict__ gscale, T* __restrict__ dx, long ldo, int B, int D) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float gs = gscale ? expf(*gscale) : 1.0f;
+  const T* xr = x + row * ldx;
+  const T* gr = dxhat + row * ldg;
+  float ss = 0.f, dot = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = static_cast<float>(xr[d]), g = static_cast<float>(gr[d]) * gs;
+    ss = fmaf(v, v, ss);
+    dot = fmaf(v, g, dot);
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float r = rsqrtf(ss);
+  const float k = dot * r * r;          // (x^ . g) / |x|  expressed on the un-normalised x
+  for (int d = lane; d < D; d += 32) {
+    const float v = static_cast<float>(xr[d]), g = static_cast<float>(gr[d]) * gs;
+    dx[row * ldo + d] = static_cast<T>((g - v * k) * r);
+  }
+}
+
 int check_launch(const char* what) {
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -1015,6 +1167,46 @@ int temporal_decode(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv,
   else cudaLaunchKernelEx(&lc.cfg, temporal_decode_kernel<__half>, tmK, tmV, a, reinterpret_cast<__half*>(kcache),
                           reinterpret_cast<__half*>(vcache), Tcap);
   return check_launch("temporal_decode");
+}
+
+int l2norm_backward(cudaStream_t stream, int dtype, const void* x, int ldx, const void* dxhat, int ldg, const float* gscale,
+                    void* dx, int ldo, int B, int D) {
+  if (B <= 0) return 0;
+  if (dtype != kBF16 && dtype != kF16) { set_error("l2norm_backward: dtype must be bf16/f16"); return -1; }
+  LaunchCfg lc(dim3(static_cast<unsigned>((B + 3) / 4)), dim3(128), 0, stream);
+  ProfScope ps(stream, kProfOther, 0.0, 6.0 * B * D);
+  if (dtype == kBF16)
+    cudaLaunchKernelEx(&lc.cfg, l2norm_bwd_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(x), static_cast<long>(ldx),
+                       reinterpret_cast<const __nv_bfloat16*>(dxhat), static_cast<long>(ldg), gscale, reinterpret_cast<__nv_bfloat16*>(dx),
+                       static_cast<long>(ldo), B, D);
+  else
+    cudaLaunchKernelEx(&lc.cfg, l2norm_bwd_kernel<__half>, reinterpret_cast<const __half*>(x), static_cast<long>(ldx),
+                       reinterpret_cast<const __half*>(dxhat), static_cast<long>(ldg), gscale, reinterpret_cast<__half*>(dx),
+                       static_cast<long>(ldo), B, D);
+  return check_launch("l2norm_backward");
+}
+
+int siglip_head(cudaStream_t stream, int dtype, const void* image, int ld_i, const void* text, int ld_t, int B, int L, int D,
+                const float* logit_scale, const float* logit_bias, int norm_image, int norm_text, const long long* targets,
+                int diag_offset, float loss_div, float* logits, int ld_l, float* loss, void* dlogits, int ld_d, float* dparams) {
+  if (B <= 0 || L <= 0) return 0;
+  if (dtype != kBF16 && dtype != kF16) { set_error("siglip_head: dtype must be bf16/f16"); return -1; }
+  if (!image || !text || !logit_scale || !loss) { set_error("siglip_head: null argument"); return -1; }
+  if ((D % 8) || (ld_i % 8) || (ld_t % 8) || ((reinterpret_cast<uintptr_t>(image) | reinterpret_cast<uintptr_t>(text)) & 15)) {
+    set_error("siglip_head: D and the leading dims must be multiples of 8, 16-byte aligned rows (D=%d ld_i=%d ld_t=%d)", D, ld_i, ld_t);
+    return -1;
+  }
+  if (!(loss_div > 0.f)) { set_error("siglip_head: loss divisor must be positive"); return -1; }
+  HeadArgs a;
+  a.image = image; a.ld_i = ld_i; a.text = text; a.ld_t = ld_t; a.B = B; a.L = L; a.D = D;
+  a.logit_scale = logit_scale; a.logit_bias = logit_bias; a.norm_image = norm_image; a.norm_text = norm_text;
+  a.targets = targets; a.diag_offset = diag_offset; a.loss_scale = 1.0f / loss_div;
+  a.logits = logits; a.ld_l = ld_l; a.loss = loss; a.dlogits = dlogits; a.ld_d = ld_d; a.dparams = dparams;
+  ProfScope ps(stream, kProfOther, 2.0 * B * L * static_cast<double>(D), 2.0 * (static_cast<double>(B) + L) * D + 4.0 * B * L);
+  LaunchCfg lc(dim3(static_cast<unsigned>((B + 15) / 16), static_cast<unsigned>((L + 127) / 128)), dim3(128), 0, stream);
+  if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, siglip_head_kernel<__nv_bfloat16>, a);
+  else cudaLaunchKernelEx(&lc.cfg, siglip_head_kernel<__half>, a);
+  return check_launch("siglip_head");
 }
 
 int kv_append(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache,

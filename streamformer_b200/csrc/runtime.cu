@@ -1274,6 +1274,18 @@ int sf_op_temporal_decode(void* stream, int dtype, const void* qkv, int ld_qkv, 
   return temporal_decode(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, kcache, vcache, Tcap, out, ld_out, sites,
                          heads, seen, scale);
 }
+int sf_op_siglip_head(void* stream, int dtype, const void* image, int ld_i, const void* text, int ld_t, int B, int L, int D,
+                      const float* logit_scale, const float* logit_bias, int normalize_image, int normalize_text,
+                      const int64_t* targets, int diag_offset, float loss_div, float* logits, int ld_logits, float* loss,
+                      void* dlogits, int ld_dlogits, float* dparams) {
+  return siglip_head(static_cast<cudaStream_t>(stream), dtype, image, ld_i, text, ld_t, B, L, D, logit_scale, logit_bias,
+                     normalize_image, normalize_text, reinterpret_cast<const long long*>(targets), diag_offset, loss_div, logits,
+                     ld_logits, loss, dlogits, ld_dlogits, dparams);
+}
+int sf_op_l2norm_backward(void* stream, int dtype, const void* x, int ldx, const void* dxhat, int ldg, const float* gscale,
+                          void* dx, int ldo, int B, int D) {
+  return l2norm_backward(static_cast<cudaStream_t>(stream), dtype, x, ldx, dxhat, ldg, gscale, dx, ldo, B, D);
+}
 int sf_op_kv_append(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache, int Tcap, int sites,
                     int heads, int Tq, int pos0) {
   return kv_append(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, kcache, vcache, Tcap, sites, heads, Tq, pos0);

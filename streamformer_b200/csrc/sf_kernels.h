@@ -150,6 +150,18 @@ int pool_attention(cudaStream_t stream, int dtype, const void* kv, int ld_kv, co
 int pool_probe(cudaStream_t stream, int dtype, const void* tokens, int ld, const float* u, const void* wv, const float* bv,
                void* out, int ld_out, int frames, int heads, int S);
 
+// SigLIP task head on the (gathered) last-frame pooler_output: logits = exp(*logit_scale) * <x^, t^> + *logit_bias,
+// loss += sum(-logsigmoid(label * logit)) / loss_div, optionally d loss / d logits and the two scalar parameter
+// gradients (attention.cu).  Labels: +1 at targets[i] (classification) or at column i + diag_offset (contrastive;
+// diag_offset < 0: negatives only), -1 elsewhere.  `loss` and `dparams` are accumulated into (zero them first).
+int siglip_head(cudaStream_t stream, int dtype, const void* image, int ld_i, const void* text, int ld_t, int B, int L, int D,
+                const float* logit_scale, const float* logit_bias, int norm_image, int norm_text, const long long* targets,
+                int diag_offset, float loss_div, float* logits, int ld_l, float* loss, void* dlogits, int ld_d, float* dparams);
+
+// dx = (g - x^ (x^ . g)) / |x| with g = exp(*gscale) * dxhat: backward of x^ = x / |x| (rows of [B, D])
+int l2norm_backward(cudaStream_t stream, int dtype, const void* x, int ldx, const void* dxhat, int ldg, const float* gscale,
+                    void* dx, int ldo, int B, int D);
+
 // out = cast(in)  (weight / bias packing helpers; n elements)
 int cast(cudaStream_t stream, int src_dtype, const void* src, int dst_dtype, void* dst, size_t n);
 
