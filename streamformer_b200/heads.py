@@ -50,8 +50,8 @@ class _SiglipHeadFn(torch.autograd.Function):
         B, D = image.shape
         L = text.shape[0]
         dev = image.device
-        scale = logit_scale.detach().float().reshape(1).contiguous()
-        bias = logit_bias.detach().float().reshape(1).contiguous() if logit_bias is not None else None
+        scale = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        bias = logit_bias.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous() if logit_bias is not None else None
         logits = torch.empty(B, L, dtype=torch.float32, device=dev) if want_logits else None
         loss = torch.zeros(1, dtype=torch.float32, device=dev)
         needs_grad = any(ctx.needs_input_grad[:4])
@@ -96,8 +96,8 @@ class _SiglipHeadFn(torch.autograd.Function):
             else:
                 g_image = (dxhat.float() * scale.exp()).to(dt)
             g_image = g_image * g_loss.to(dt)
-        g_scale = (dparams[0] * g_loss).reshape(()) if ctx.needs_input_grad[2] else None
-        g_bias = (dparams[1] * g_loss).reshape(()) if (has_bias and ctx.needs_input_grad[3]) else None
+        g_scale = (dparams[0] * g_loss.to(dparams.device)).reshape(()) if ctx.needs_input_grad[2] else None
+        g_bias = (dparams[1] * g_loss.to(dparams.device)).reshape(()) if (has_bias and ctx.needs_input_grad[3]) else None
         return g_image, None, g_scale, g_bias, None, None, None, None, None, None
 
 
@@ -131,10 +131,11 @@ class TimesformerVideoClassificationHead(nn.Module):
 
     def prepare_multi_task(self, text_encoder=None, text_tokenizer=None, logit_scale=None, logit_bias=None, vision_model=None,
                            label_embeddings: Optional[torch.Tensor] = None):
+        dev = self.logit_scale.device
         if logit_scale is not None:
-            self.logit_scale = nn.Parameter(logit_scale.detach().clone().reshape(()))
+            self.logit_scale = nn.Parameter(logit_scale.detach().clone().reshape(()).to(dev))
         if logit_bias is not None:
-            self.logit_bias = nn.Parameter(logit_bias.detach().clone().reshape(()))
+            self.logit_bias = nn.Parameter(logit_bias.detach().clone().reshape(()).to(dev))
         if label_embeddings is None:
             raise NotImplementedError("the SigLIP text tower is outside this repo's scope (SURVEY §8): pass label_embeddings=[L, D]")
         self.set_label_embeddings(label_embeddings)
