@@ -251,6 +251,53 @@ int sf_op_siglip_head(void* stream, int dtype, const void* image, int ld_i, cons
 int sf_op_l2norm_backward(void* stream, int dtype, const void* x, int ldx, const void* dxhat, int ldg,
                           const float* gscale, void* dx, int ldo, int B, int D);
 
+/* ---- backward pass: what torch.autograd does for the reference's training step
+ * (tools/finetune_tools.py:543-573) on the graph of …siglip.py:900-1004.  The contractions (dgrad = dY . W,
+ * wgrad = dY^T . X) run on sf_op_gemm, fed by sf_op_transpose; the rest are the row-wise / attention kernels
+ * below.  streamformer_b200/autograd.py composes them into one torch.autograd.Function around the forward. */
+/* packed matrices / vectors of the bound context copied (transposed when `transpose`) into caller memory:
+ * name in {"t_qkv","t_out","t_dense","s_qkv","s_out","fc1","fc2"} (layer matrices as the kernels consume them:
+ * LayerNorm gamma folded in, LoRA merged; [out, in] row-major, activation dtype), the same with suffix "_b"
+ * (fp32 bias vectors, folded where the matrix is), layer = -1 for {"head_kv","head_out","head_fc1","head_fc2",
+ * "patch"} and their "_b", and "head_q" (fp32 [D], the scaled probe query). */
+int sf_export_packed(sf_ctx* ctx, void* stream, int layer, const char* name, int transpose, void* dst, size_t dst_bytes);
+/* out[n, m] = in[m, n]; out row stride ld_out >= round_up(M, 8), the padding columns are zeroed */
+int sf_op_transpose(void* stream, int dtype, const void* in, int ld_in, void* out, int ld_out, int M, int N);
+/* out[n] = sum_m x[m, n]  (fp32) */
+int sf_op_colsum(void* stream, int dtype, const void* x, int ld, int M, int N, float* out);
+/* LayerNorm without affine, n = (x - mean) rstd:  dx = rstd (dn - mean(dn) - n mean(dn n)) + dres (dres nullable) */
+int sf_op_ln_backward(void* stream, int dtype, const void* x, int ldx, const void* dn, int ld_dn, float eps,
+                      const void* dres, int ld_dres, void* dx, int ld_dx, int M, int D);
+/* LayerNorm with gamma / beta, y[row_map(m)] = LN(x[m]):  dx, dgamma += sum dy n, dbeta += sum dy (fp32, accumulated) */
+int sf_op_ln_affine_backward(void* stream, int dtype, const void* x, int ldx, const void* dy, int ld_dy,
+                             const float* gamma, float eps, void* dx, int ld_dx, int M, int D, int row_map, int T, int S,
+                             float* dgamma, float* dbeta);
+/* in place: a -> h = GELU(a), dh -> dpre = dh GELU'(a)   (n elements, multiple of 8; act as sf_act) */
+int sf_op_gelu_backward(void* stream, int dtype, void* a_h, void* dh_dpre, long long n, int act);
+/* dy = tanh(*gate) dx;  *dgate += (1 - tanh^2(*gate)) <dx, y>   (…siglip.py:954-958) */
+int sf_op_gate_backward(void* stream, int dtype, const void* dx, const void* y, const float* gate, void* dy, long long n,
+                        float* dgate);
+/* parameter gradients of a Linear whose input LayerNorm is folded into it, from G = dY^T . n [O, I] and db [O]:
+ * dW = G gamma + db (x) beta (out_dtype), dgamma += colsum(G o W), dbeta += W^T db with W = Wp / gamma;
+ * gamma == NULL: plain Linear (dW = G cast to out_dtype) */
+int sf_op_wfold_finish(void* stream, int dtype, const void* G, int ldg, const void* Wp, int ldw, const float* gamma,
+                       const float* beta, const float* db, void* dW, int out_dtype, int ld_dw, int O, int I,
+                       float* dgamma, float* dbeta);
+/* gradients of the embedding tables from dx [B, S*T, D] (rows (b,n,t)): mode 0 position table [S, D],
+ * mode 1 time table (out[tidx[t]] += ...), fp32, accumulated */
+int sf_op_embed_table_grad(void* stream, int dtype, const void* dx, int ld, int B, int T, int S, int D, int mode,
+                           const int* tidx, float* out);
+/* out[row_map(m)] = in[m] (rows of row_bytes bytes, multiple of 16) */
+int sf_op_rowperm(void* stream, const void* in, void* out, long long M, int row_bytes, int row_map, int T, int S);
+/* backward of the temporal (mode 0: groups = sites, L = T) or spatial (mode 1: groups = frames, L = S, rows as in
+ * sf_op_spatial_attention) attention core: dqkv (dq|dk|dv, layout of qkv) from qkv, the forward output and dout */
+int sf_op_attention_backward(void* stream, int dtype, int mode, const void* qkv, int ld_qkv, const void* out, int ld_out,
+                             const void* dout, int ld_dout, void* dqkv, int ld_dqkv, int groups, int heads, int L,
+                             int T_inner, int causal, float scale);
+/* backward of sf_op_pool_attention: dkv [frames*S, 2*heads*64], dq fp32 [heads*64] accumulated (nullable) */
+int sf_op_pool_attention_backward(void* stream, int dtype, const void* kv, int ld_kv, const float* q, const void* dout,
+                                  int ld_dout, void* dkv, int ld_dkv, float* dq, int frames, int heads, int S);
+
 #ifdef __cplusplus
 }
 #endif

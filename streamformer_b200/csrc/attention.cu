@@ -1045,6 +1045,294 @@ __global__ void __launch_bounds__(128) l2norm_bwd_kernel(const T* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------------------- attention backward
+// Backward of softmax(scale Q K^T [+ causal mask]) V for both attention cores of a layer:
+//   temporal: one task = (site, head), L = T frames, rows consecutive               (…siglip.py:575-615)
+//   spatial : one task = (frame, head), L = S tokens, rows T_inner apart in the (b,n,t) stream  (…siglip.py:688-717)
+// All of Q, K, V, dO of a task sit in shared memory (128B-swizzled 16-row tiles); probabilities are recomputed
+// (never stored by the forward), so the kernel makes two passes without any atomics:
+//   pass 1, warp = 16-query tile:  row log-sum-exp, then dS = P o (dO V^T - D), dQ = scale dS K
+//   pass 2, warp = 16-key tile  :  P^T, dS^T recomputed against every query tile, dV = P^T dO, dK = scale dS^T Q
+// with D_i = <dO_i, O_i>.  Tensor-core work on mma.sync m16n8k16 (fp32 accumulate), P / dS rounded to the 16-bit
+// operand type between the two contractions exactly as the forward rounds P.
+struct AttnBwdArgs {
+  const void* qkv; long ld;          // q | k | v column blocks of width heads*64
+  const void* out; long ld_o;        // forward output (ctx)
+  const void* dout; long ld_do;
+  void* dqkv; long ld_dq;            // dq | dk | dv, same layout as qkv
+  int L, heads, T_inner, S, mode, causal;
+  long tasks;
+  float scale, scale_log2;
+};
+
+template <typename T, int kTiles, int kTasksPerCta>
+__global__ void __launch_bounds__(kTiles * kTasksPerCta * 32) attn_bwd_kernel(const AttnBwdArgs a) {
+  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+  constexpr int Lp = kTiles * 16;
+  constexpr int kTileBytes = Lp * 128;
+  constexpr int kTaskBytes = 4 * kTileBytes + 2 * Lp * 4;
+  extern __shared__ uint8_t bsm_raw[];
+  uint8_t* bsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bsm_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  griddep_wait();
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int slot = warp / kTiles, tw = warp % kTiles;           // task slot inside the CTA, tile owned by this warp
+  const long task = static_cast<long>(blockIdx.x) * kTasksPerCta + slot;
+  const bool live = task < a.tasks;
+  uint8_t* base = bsm + static_cast<size_t>(slot) * ((kTaskBytes + 1023) / 1024 * 1024);
+  uint8_t *Qs = base, *Ks = base + kTileBytes, *Vs = base + 2 * kTileBytes, *Gs = base + 3 * kTileBytes;
+  float* Lse = reinterpret_cast<float*>(base + 4 * kTileBytes);
+  float* Dv = Lse + Lp;
+  const int D = a.heads * kHd;
+  const long grp = live ? task / a.heads : 0;
+  const int h = live ? static_cast<int>(task % a.heads) : 0;
+  long row0, rstride;
+  if (a.mode == 0) { row0 = grp * a.L; rstride = 1; }
+  else if (a.T_inner > 1) { row0 = (grp / a.T_inner) * a.S * a.T_inner + grp % a.T_inner; rstride = a.T_inner; }
+  else { row0 = grp * a.S; rstride = 1; }
+  const T* qkv = reinterpret_cast<const T*>(a.qkv);
+  const T* dO = reinterpret_cast<const T*>(a.dout);
+  const T* Og = reinterpret_cast<const T*>(a.out);
+  // ---- stage Q, K, V, dO (rows >= L zero-filled)
+  for (int i = tw * 32 + lane; i < Lp * 8; i += kTiles * 32) {
+    const int r = i >> 3, ch = i & 7;
+    const bool ok = live && r < a.L;
+    const long grow = row0 + static_cast<long>(ok ? r : 0) * rstride;
+    const T* src = qkv + grow * a.ld + h * kHd + ch * 8;
+    cp_async_16(Qs + tile_off(r, ch), src, ok);
+    cp_async_16(Ks + tile_off(r, ch), src + D, ok);
+    cp_async_16(Vs + tile_off(r, ch), src + 2 * D, ok);
+    cp_async_16(Gs + tile_off(r, ch), dO + grow * a.ld_do + h * kHd + ch * 8, ok);
+  }
+  cp_async_commit();
+  // D_i = <dO_i, O_i> for the rows of this warp's tile (straight from global memory)
+  for (int rr = 0; rr < 16; ++rr) {
+    const int r = tw * 16 + rr;
+    float d = 0.f;
+    if (live && r < a.L) {
+      const long grow = row0 + static_cast<long>(r) * rstride;
+      const float2 x = Pack2<T>::unpack(*reinterpret_cast<const uint32_t*>(dO + grow * a.ld_do + h * kHd + 2 * lane));
+      const float2 y = Pack2<T>::unpack(*reinterpret_cast<const uint32_t*>(Og + grow * a.ld_o + h * kHd + 2 * lane));
+      d = warp_sum(x.x * y.x + x.y * y.y);
+    }
+    if (lane == 0) Dv[r] = d;
+  }
+  cp_async_wait<0>();
+  if constexpr (kTiles * kTasksPerCta > 1) __syncthreads(); else __syncwarp();
+  const uint32_t q_u = smem_u32(Qs), k_u = smem_u32(Ks), v_u = smem_u32(Vs), g_u = smem_u32(Gs);
+  const int ntiles = (a.L + 15) >> 4;
+  T* dq_out = reinterpret_cast<T*>(a.dqkv);
+
+  auto load_a = [&](uint32_t (&fr)[4][4], uint32_t tile_u, int r0) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(fr[ks], tile_u + tile_off(r0 + (lane & 15), 2 * ks + (lane >> 4)));
+  };
+  // scaled + masked scores of a 16 x 16 block: rows i0+g / i0+g+8 (fragment halves), columns j0 + ...
+  auto mask_scale = [&](float (&s0)[4], float (&s1)[4], int i0, int j0, bool rows_are_queries) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ri = i0 + g + ((e >> 1) << 3);
+      const int c0 = j0 + 2 * c + (e & 1), c1 = c0 + 8;
+      const int q0 = rows_are_queries ? ri : c0, k0 = rows_are_queries ? c0 : ri;
+      const int q1 = rows_are_queries ? ri : c1, k1 = rows_are_queries ? c1 : ri;
+      const bool ok0 = k0 < a.L && (!a.causal || k0 <= q0);
+      const bool ok1 = k1 < a.L && (!a.causal || k1 <= q1);
+      s0[e] = ok0 ? s0[e] * a.scale_log2 : -INFINITY;
+      s1[e] = ok1 ? s1[e] * a.scale_log2 : -INFINITY;
+    }
+  };
+
+  if (live && tw < ntiles) {
+    // ================================================================ pass 1: this warp's 16 queries
+    const int i0 = tw * 16;
+    uint32_t qa[4][4], ga[4][4];
+    load_a(qa, q_u, i0);
+    load_a(ga, g_u, i0);
+    const int kend = a.causal ? tw + 1 : ntiles;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    for (int kb = 0; kb < kend; ++kb) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      qk_16keys<kBf16>(s0, s1, qa, k_u, kb * 16, lane);
+      mask_scale(s0, s1, i0, kb * 16, true);
+      float mx0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
+      float mx1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m_run[0], mx0), mn1 = fmaxf(m_run[1], mx1);
+      const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0, mu1 = (mn1 == -INFINITY) ? 0.f : mn1;
+      float p0 = exp2f(s0[0] - mu0) + exp2f(s0[1] - mu0) + exp2f(s1[0] - mu0) + exp2f(s1[1] - mu0);
+      float p1 = exp2f(s0[2] - mu1) + exp2f(s0[3] - mu1) + exp2f(s1[2] - mu1) + exp2f(s1[3] - mu1);
+      p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+      p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+      l_run[0] = l_run[0] * exp2f(m_run[0] - mu0) + p0;
+      l_run[1] = l_run[1] * exp2f(m_run[1] - mu1) + p1;
+      m_run[0] = mn0; m_run[1] = mn1;
+    }
+    const float lse0 = m_run[0] + log2f(l_run[0]), lse1 = m_run[1] + log2f(l_run[1]);
+    if (c == 0) { Lse[i0 + g] = lse0; Lse[i0 + g + 8] = lse1; }
+    const float d0 = Dv[i0 + g], d1 = Dv[i0 + g + 8];
+    float dq[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) { dq[d][0] = dq[d][1] = dq[d][2] = dq[d][3] = 0.f; }
+    for (int kb = 0; kb < kend; ++kb) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+      qk_16keys<kBf16>(s0, s1, qa, k_u, kb * 16, lane);
+      mask_scale(s0, s1, i0, kb * 16, true);
+      qk_16keys<kBf16>(t0, t1, ga, v_u, kb * 16, lane);                  // dP = dO V^T
+      float e0[4], e1[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float ls = (e < 2) ? lse0 : lse1, dd = (e < 2) ? d0 : d1;
+        e0[e] = exp2f(s0[e] - ls) * (t0[e] - dd);                        // dS = P o (dP - D)
+        e1[e] = exp2f(s1[e] - ls) * (t1[e] - dd);
+      }
+      uint32_t pa[4];
+      pa[0] = Pack2<T>::pack(e0[0], e0[1]); pa[1] = Pack2<T>::pack(e0[2], e0[3]);
+      pa[2] = Pack2<T>::pack(e1[0], e1[1]); pa[3] = Pack2<T>::pack(e1[2], e1[3]);
+      pv_16keys<kBf16>(dq, pa, k_u, kb * 16, lane);                      // dQ += dS K
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = i0 + g + half * 8;
+      if (r < a.L) {
+        T* dst = dq_out + (row0 + static_cast<long>(r) * rstride) * a.ld_dq + h * kHd;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+          *reinterpret_cast<uint32_t*>(dst + d * 8 + 2 * c) = Pack2<T>::pack(dq[d][2 * half] * a.scale, dq[d][2 * half + 1] * a.scale);
+      }
+    }
+  }
+  if constexpr (kTiles * kTasksPerCta > 1) __syncthreads(); else __syncwarp();
+  if (live && tw < ntiles) {
+    // ================================================================ pass 2: this warp's 16 keys
+    const int j0 = tw * 16;
+    uint32_t ka[4][4], va[4][4];
+    load_a(ka, k_u, j0);
+    load_a(va, v_u, j0);
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) { dk[d][0] = dk[d][1] = dk[d][2] = dk[d][3] = 0.f; dv[d][0] = dv[d][1] = dv[d][2] = dv[d][3] = 0.f; }
+    const int qbeg = a.causal ? tw : 0;
+    for (int qb = qbeg; qb < ntiles; ++qb) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+      qk_16keys<kBf16>(s0, s1, ka, q_u, qb * 16, lane);                  // S^T block: rows = keys, columns = queries
+      mask_scale(s0, s1, j0, qb * 16, false);
+      qk_16keys<kBf16>(t0, t1, va, g_u, qb * 16, lane);                  // dP^T = V dO^T
+      float p0[4], p1[4], e0[4], e1[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q0 = qb * 16 + 2 * c + (e & 1), q1 = q0 + 8;
+        p0[e] = exp2f(s0[e] - Lse[q0]);
+        p1[e] = exp2f(s1[e] - Lse[q1]);
+        e0[e] = p0[e] * (t0[e] - Dv[q0]);
+        e1[e] = p1[e] * (t1[e] - Dv[q1]);
+      }
+      uint32_t pa[4];
+      pa[0] = Pack2<T>::pack(p0[0], p0[1]); pa[1] = Pack2<T>::pack(p0[2], p0[3]);
+      pa[2] = Pack2<T>::pack(p1[0], p1[1]); pa[3] = Pack2<T>::pack(p1[2], p1[3]);
+      pv_16keys<kBf16>(dv, pa, g_u, qb * 16, lane);                      // dV += P^T dO
+      pa[0] = Pack2<T>::pack(e0[0], e0[1]); pa[1] = Pack2<T>::pack(e0[2], e0[3]);
+      pa[2] = Pack2<T>::pack(e1[0], e1[1]); pa[3] = Pack2<T>::pack(e1[2], e1[3]);
+      pv_16keys<kBf16>(dk, pa, q_u, qb * 16, lane);                      // dK += dS^T Q
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = j0 + g + half * 8;
+      if (r < a.L) {
+        T* dst = dq_out + (row0 + static_cast<long>(r) * rstride) * a.ld_dq + h * kHd;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          *reinterpret_cast<uint32_t*>(dst + D + d * 8 + 2 * c) = Pack2<T>::pack(dk[d][2 * half] * a.scale, dk[d][2 * half + 1] * a.scale);
+          *reinterpret_cast<uint32_t*>(dst + 2 * D + d * 8 + 2 * c) = Pack2<T>::pack(dv[d][2 * half], dv[d][2 * half + 1]);
+        }
+      }
+    }
+  }
+}
+
+// Backward of the pooling attention of the SigLIP head (one learned probe as the only query, …siglip.py:1141-1148):
+// per (frame, head): p = softmax_n(q . K_n), out = sum_n p_n V_n.  One warp per task; lane owns keys lane, lane+32, ...
+//   dV_n = p_n dout, dK_n = ds_n q, dq += sum_n ds_n K_n with ds = p o (dout . V_n - sum_m p_m dout . V_m)
+template <typename T>
+__global__ void __launch_bounds__(128) pool_attn_bwd_kernel(const T* __restrict__ kv, long ld_kv, const float* __restrict__ q,
+                                                            const T* __restrict__ dout, long ld_do, T* __restrict__ dkv, long ld_dkv,
+                                                            float* __restrict__ dq, int frames, int heads, int S) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long task = static_cast<long>(blockIdx.x) * 4 + warp;
+  if (task >= static_cast<long>(frames) * heads) return;
+  const int f = static_cast<int>(task / heads), h = static_cast<int>(task % heads);
+  const int D = heads * kHd;
+  constexpr int kMaxPer = 32;                                    // S <= 1024
+  float sc[kMaxPer], dp[kMaxPer];
+  const float* qh = q + h * kHd;
+  const T* go = dout + static_cast<long>(f) * ld_do + h * kHd;
+  float mx = -INFINITY;
+  int cnt = 0;
+  for (int n = lane; n < S; n += 32, ++cnt) {
+    const T* kr = kv + (static_cast<long>(f) * S + n) * ld_kv + h * kHd;
+    float s = 0.f, d = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      float kf[8], vf[8], gf[8];
+      const uint4 ku = *reinterpret_cast<const uint4*>(kr + ch * 8), vu = *reinterpret_cast<const uint4*>(kr + D + ch * 8);
+      const uint4 gu = *reinterpret_cast<const uint4*>(go + ch * 8);
+      const uint32_t kw[4] = {ku.x, ku.y, ku.z, ku.w}, vw[4] = {vu.x, vu.y, vu.z, vu.w}, gw[4] = {gu.x, gu.y, gu.z, gu.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = Pack2<T>::unpack(kw[e]), b = Pack2<T>::unpack(vw[e]), cc = Pack2<T>::unpack(gw[e]);
+        kf[2 * e] = a.x; kf[2 * e + 1] = a.y; vf[2 * e] = b.x; vf[2 * e + 1] = b.y; gf[2 * e] = cc.x; gf[2 * e + 1] = cc.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s = fmaf(kf[e], qh[ch * 8 + e], s); d = fmaf(vf[e], gf[e], d); }
+    }
+    sc[cnt] = s; dp[cnt] = d;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float l = 0.f;
+  for (int i = 0; i < cnt; ++i) { sc[i] = __expf(sc[i] - mx); l += sc[i]; }
+  l = warp_sum(l);
+  const float inv = 1.0f / l;
+  float pd = 0.f;
+  for (int i = 0; i < cnt; ++i) { sc[i] *= inv; pd = fmaf(sc[i], dp[i], pd); }
+  pd = warp_sum(pd);
+  float dqa[kHd];
+#pragma unroll
+  for (int e = 0; e < kHd; ++e) dqa[e] = 0.f;
+  cnt = 0;
+  for (int n = lane; n < S; n += 32, ++cnt) {
+    const float p = sc[cnt], ds = p * (dp[cnt] - pd);
+    const T* kr = kv + (static_cast<long>(f) * S + n) * ld_kv + h * kHd;
+    T* dr = dkv + (static_cast<long>(f) * S + n) * ld_dkv + h * kHd;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const uint4 ku = *reinterpret_cast<const uint4*>(kr + ch * 8), gu = *reinterpret_cast<const uint4*>(go + ch * 8);
+      const uint32_t kw[4] = {ku.x, ku.y, ku.z, ku.w}, gw[4] = {gu.x, gu.y, gu.z, gu.w};
+      uint32_t ok[4], ov[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = Pack2<T>::unpack(kw[e]), cc = Pack2<T>::unpack(gw[e]);
+        dqa[ch * 8 + 2 * e] = fmaf(ds, a.x, dqa[ch * 8 + 2 * e]);
+        dqa[ch * 8 + 2 * e + 1] = fmaf(ds, a.y, dqa[ch * 8 + 2 * e + 1]);
+        ok[e] = Pack2<T>::pack(ds * qh[ch * 8 + 2 * e], ds * qh[ch * 8 + 2 * e + 1]);
+        ov[e] = Pack2<T>::pack(p * cc.x, p * cc.y);
+      }
+      *reinterpret_cast<uint4*>(dr + ch * 8) = make_uint4(ok[0], ok[1], ok[2], ok[3]);
+      *reinterpret_cast<uint4*>(dr + D + ch * 8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+    }
+  }
+  if (dq) {
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) {
+      const float v = warp_sum(dqa[e]);
+      if (lane == 0) atomicAdd(dq + h * kHd + e, v);
+    }
+  }
+}
+
 int check_launch(const char* what) {
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -1167,6 +1455,62 @@ int temporal_decode(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv,
   else cudaLaunchKernelEx(&lc.cfg, temporal_decode_kernel<__half>, tmK, tmV, a, reinterpret_cast<__half*>(kcache),
                           reinterpret_cast<__half*>(vcache), Tcap);
   return check_launch("temporal_decode");
+}
+
+template <typename T, int kTiles, int kTasksPerCta>
+static int launch_attn_bwd(cudaStream_t stream, const AttnBwdArgs& a) {
+  constexpr int Lp = kTiles * 16;
+  constexpr int kTaskBytes = ((4 * Lp * 128 + 2 * Lp * 4) + 1023) / 1024 * 1024;
+  constexpr int smem = kTaskBytes * kTasksPerCta + 1024;
+  auto kernel = attn_bwd_kernel<T, kTiles, kTasksPerCta>;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  const long blocks = (a.tasks + kTasksPerCta - 1) / kTasksPerCta;
+  LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(kTiles * kTasksPerCta * 32), smem, stream);
+  cudaLaunchKernelEx(&lc.cfg, kernel, a);
+  return check_launch("attention_backward");
+}
+
+// mode 0: temporal (groups = sites, L = T frames); mode 1: spatial (groups = frames, L = S tokens, rows as in spatial_attention)
+int attention_backward(cudaStream_t stream, int dtype, int mode, const void* qkv, int ld_qkv, const void* out, int ld_o, const void* dout,
+                       int ld_do, void* dqkv, int ld_dq, int groups, int heads, int L, int T_inner, int causal, float scale) {
+  if (groups <= 0 || L <= 0) return 0;
+  if (dtype != kBF16 && dtype != kF16) { set_error("attention_backward: dtype must be bf16/f16"); return -1; }
+  if ((ld_qkv % 8) || (ld_do % 8) || (ld_o % 2) || (ld_dq % 2)) { set_error("attention_backward: bad leading dims"); return -1; }
+  if (L > 208) { set_error("attention_backward: %d tokens per attention group exceed the 208 this round's backward kernel stages in shared memory", L); return -1; }
+  AttnBwdArgs a;
+  a.qkv = qkv; a.ld = ld_qkv; a.out = out; a.ld_o = ld_o; a.dout = dout; a.ld_do = ld_do; a.dqkv = dqkv; a.ld_dq = ld_dq;
+  a.L = L; a.heads = heads; a.T_inner = T_inner; a.S = L; a.mode = mode; a.causal = causal;
+  a.tasks = static_cast<long>(groups) * heads;
+  a.scale = scale; a.scale_log2 = scale * kLog2e;
+  ProfScope ps(stream, mode == 0 ? kProfTemporalAttn : kProfSpatialAttn, 14.0 * groups * heads * static_cast<double>(L) * L * kHd,
+               2.0 * groups * heads * kHd * 8.0 * L);
+#define SF_ABWD(TT, TP) (dtype == kBF16 ? launch_attn_bwd<__nv_bfloat16, TT, TP>(stream, a) : launch_attn_bwd<__half, TT, TP>(stream, a))
+  if (L <= 16) return SF_ABWD(1, 4);
+  if (L <= 32) return SF_ABWD(2, 2);
+  if (L <= 64) return SF_ABWD(4, 1);
+  if (L <= 128) return SF_ABWD(8, 1);
+  return SF_ABWD(13, 1);
+#undef SF_ABWD
+}
+
+int pool_attention_backward(cudaStream_t stream, int dtype, const void* kv, int ld_kv, const float* q, const void* dout, int ld_do,
+                            void* dkv, int ld_dkv, float* dq, int frames, int heads, int S) {
+  if (frames <= 0) return 0;
+  if (dtype != kBF16 && dtype != kF16) { set_error("pool_attention_backward: dtype must be bf16/f16"); return -1; }
+  if (S > 1024 || (ld_kv % 8) || (ld_do % 8) || (ld_dkv % 8)) { set_error("pool_attention_backward: S <= 1024 and 16-byte aligned rows required"); return -1; }
+  const long tasks = static_cast<long>(frames) * heads;
+  ProfScope ps(stream, kProfPoolAttn, 8.0 * tasks * S * kHd, 8.0 * tasks * S * kHd);
+  LaunchCfg lc(dim3(static_cast<unsigned>((tasks + 3) / 4)), dim3(128), 0, stream);
+  if (dtype == kBF16)
+    cudaLaunchKernelEx(&lc.cfg, pool_attn_bwd_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(kv), static_cast<long>(ld_kv), q,
+                       reinterpret_cast<const __nv_bfloat16*>(dout), static_cast<long>(ld_do), reinterpret_cast<__nv_bfloat16*>(dkv),
+                       static_cast<long>(ld_dkv), dq, frames, heads, S);
+  else
+    cudaLaunchKernelEx(&lc.cfg, pool_attn_bwd_kernel<__half>, reinterpret_cast<const __half*>(kv), static_cast<long>(ld_kv), q,
+                       reinterpret_cast<const __half*>(dout), static_cast<long>(ld_do), reinterpret_cast<__half*>(dkv), static_cast<long>(ld_dkv),
+                       dq, frames, heads, S);
+  return check_launch("pool_attention_backward");
 }
 
 int l2norm_backward(cudaStream_t stream, int dtype, const void* x, int ldx, const void* dxhat, int ldg, const float* gscale,

@@ -1286,6 +1286,99 @@ int sf_op_l2norm_backward(void* stream, int dtype, const void* x, int ldx, const
                           void* dx, int ldo, int B, int D) {
   return l2norm_backward(static_cast<cudaStream_t>(stream), dtype, x, ldx, dxhat, ldg, gscale, dx, ldo, B, D);
 }
+int sf_export_packed(sf_ctx* c, void* stream, int layer, const char* name, int transpose, void* dst, size_t dst_bytes) {
+  if (!c || !name || !dst) { set_error("sf_export_packed: null argument"); return SF_ERR_INVALID; }
+  if (!c->bound) { set_error("weights not bound"); return SF_ERR_STATE; }
+  DeviceGuard dg(c->device);
+  const long D = c->D, I = c->I, K = c->Kp;
+  const void* mat = nullptr; const float* vec = nullptr;
+  long rows = 0, cols = 0, n = 0;
+  const std::string nm(name);
+  if (layer >= 0) {
+    if (layer >= c->L || !c->have_layer[layer]) { set_error("sf_export_packed: layer %d is not bound", layer); return SF_ERR_STATE; }
+    const LayerW& lw = c->layers[layer];
+    if (nm == "t_qkv") { mat = lw.t_qkv_w; rows = 3 * D; cols = D; }
+    else if (nm == "t_out") { mat = lw.t_out_w; rows = D; cols = D; }
+    else if (nm == "t_dense") { mat = lw.t_dense_w; rows = D; cols = D; }
+    else if (nm == "s_qkv") { mat = lw.s_qkv_w; rows = 3 * D; cols = D; }
+    else if (nm == "s_out") { mat = lw.s_out_w; rows = D; cols = D; }
+    else if (nm == "fc1") { mat = lw.fc1_w; rows = I; cols = D; }
+    else if (nm == "fc2") { mat = lw.fc2_w; rows = D; cols = I; }
+    else if (nm == "t_qkv_b") { vec = lw.t_qkv_b; n = 3 * D; }
+    else if (nm == "t_out_b") { vec = lw.t_out_b; n = D; }
+    else if (nm == "t_dense_b") { vec = lw.t_dense_b; n = D; }
+    else if (nm == "s_qkv_b") { vec = lw.s_qkv_b; n = 3 * D; }
+    else if (nm == "s_out_b") { vec = lw.s_out_b; n = D; }
+    else if (nm == "fc1_b") { vec = lw.fc1_b; n = I; }
+    else if (nm == "fc2_b") { vec = lw.fc2_b; n = D; }
+  } else {
+    if (nm.rfind("head", 0) == 0 && !c->have_head) { set_error("sf_export_packed: the pooling head is not bound"); return SF_ERR_STATE; }
+    if (nm.rfind("patch", 0) == 0 && !c->have_embed) { set_error("sf_export_packed: the embeddings are not bound"); return SF_ERR_STATE; }
+    if (nm == "head_kv") { mat = c->head_kv_w; rows = 2 * D; cols = D; }
+    else if (nm == "head_out") { mat = c->head_out_w; rows = D; cols = D; }
+    else if (nm == "head_fc1") { mat = c->head_fc1_w; rows = I; cols = D; }
+    else if (nm == "head_fc2") { mat = c->head_fc2_w; rows = D; cols = I; }
+    else if (nm == "patch") { mat = c->patch_w; rows = D; cols = K; }
+    else if (nm == "head_kv_b") { vec = c->head_kv_b; n = 2 * D; }
+    else if (nm == "head_out_b") { vec = c->head_out_b; n = D; }
+    else if (nm == "head_fc1_b") { vec = c->head_fc1_b; n = I; }
+    else if (nm == "head_fc2_b") { vec = c->head_fc2_b; n = D; }
+    else if (nm == "patch_b") { vec = c->patch_b; n = D; }
+    else if (nm == "head_q") { vec = c->head_q; n = D; }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec) {
+    if (dst_bytes < static_cast<size_t>(n) * 4) { set_error("sf_export_packed: destination too small for '%s'", name); return SF_ERR_INVALID; }
+    SF_CUDA(cudaMemcpyAsync(dst, vec, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (!mat) { set_error("sf_export_packed: unknown tensor '%s' (layer %d)", name, layer); return SF_ERR_INVALID; }
+  if (dst_bytes < static_cast<size_t>(rows) * cols * 2) { set_error("sf_export_packed: destination too small for '%s'", name); return SF_ERR_INVALID; }
+  if (!transpose) {
+    SF_CUDA(cudaMemcpyAsync(dst, mat, static_cast<size_t>(rows) * cols * 2, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  return transpose2d(st, c->cfg.dtype, mat, static_cast<int>(cols), dst, static_cast<int>(rows), static_cast<int>(rows), static_cast<int>(cols));
+}
+int sf_op_transpose(void* stream, int dtype, const void* in, int ld_in, void* out, int ld_out, int M, int N) {
+  return transpose2d(static_cast<cudaStream_t>(stream), dtype, in, ld_in, out, ld_out, M, N);
+}
+int sf_op_colsum(void* stream, int dtype, const void* x, int ld, int M, int N, float* out) {
+  return colsum(static_cast<cudaStream_t>(stream), dtype, x, ld, M, N, out);
+}
+int sf_op_ln_backward(void* stream, int dtype, const void* x, int ldx, const void* dn, int ld_dn, float eps, const void* dres,
+                      int ld_dres, void* dx, int ld_dx, int M, int D) {
+  return ln_backward(static_cast<cudaStream_t>(stream), dtype, x, ldx, dn, ld_dn, eps, dres, ld_dres, dx, ld_dx, M, D);
+}
+int sf_op_ln_affine_backward(void* stream, int dtype, const void* x, int ldx, const void* dy, int ld_dy, const float* gamma, float eps,
+                             void* dx, int ld_dx, int M, int D, int row_map, int T, int S, float* dgamma, float* dbeta) {
+  return ln_affine_backward(static_cast<cudaStream_t>(stream), dtype, x, ldx, dy, ld_dy, gamma, eps, dx, ld_dx, M, D, row_map, T, S, dgamma, dbeta);
+}
+int sf_op_gelu_backward(void* stream, int dtype, void* a_h, void* dh_dpre, long long n, int act) {
+  return gelu_backward(static_cast<cudaStream_t>(stream), dtype, a_h, dh_dpre, static_cast<long>(n), act);
+}
+int sf_op_gate_backward(void* stream, int dtype, const void* dx, const void* y, const float* gate, void* dy, long long n, float* dgate) {
+  return gate_backward(static_cast<cudaStream_t>(stream), dtype, dx, y, gate, dy, static_cast<long>(n), dgate);
+}
+int sf_op_wfold_finish(void* stream, int dtype, const void* G, int ldg, const void* Wp, int ldw, const float* gamma, const float* beta,
+                       const float* db, void* dW, int out_dtype, int ld_dw, int O, int I, float* dgamma, float* dbeta) {
+  return wfold_finish(static_cast<cudaStream_t>(stream), dtype, G, ldg, Wp, ldw, gamma, beta, db, dW, out_dtype, ld_dw, O, I, dgamma, dbeta);
+}
+int sf_op_embed_table_grad(void* stream, int dtype, const void* dx, int ld, int B, int T, int S, int D, int mode, const int* tidx, float* out) {
+  return embed_table_grad(static_cast<cudaStream_t>(stream), dtype, dx, ld, B, T, S, D, mode, tidx, out);
+}
+int sf_op_rowperm(void* stream, const void* in, void* out, long long M, int row_bytes, int row_map, int T, int S) {
+  return rowperm(static_cast<cudaStream_t>(stream), in, out, static_cast<long>(M), row_bytes, row_map, T, S);
+}
+int sf_op_attention_backward(void* stream, int dtype, int mode, const void* qkv, int ld_qkv, const void* out, int ld_out, const void* dout,
+                             int ld_dout, void* dqkv, int ld_dqkv, int groups, int heads, int L, int T_inner, int causal, float scale) {
+  return attention_backward(static_cast<cudaStream_t>(stream), dtype, mode, qkv, ld_qkv, out, ld_out, dout, ld_dout, dqkv, ld_dqkv, groups,
+                            heads, L, T_inner, causal, scale);
+}
+int sf_op_pool_attention_backward(void* stream, int dtype, const void* kv, int ld_kv, const float* q, const void* dout, int ld_dout,
+                                  void* dkv, int ld_dkv, float* dq, int frames, int heads, int S) {
+  return pool_attention_backward(static_cast<cudaStream_t>(stream), dtype, kv, ld_kv, q, dout, ld_dout, dkv, ld_dkv, dq, frames, heads, S);
+}
 int sf_op_kv_append(void* stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache, int Tcap, int sites,
                     int heads, int Tq, int pos0) {
   return kv_append(static_cast<cudaStream_t>(stream), dtype, qkv, ld_qkv, kcache, vcache, Tcap, sites, heads, Tq, pos0);

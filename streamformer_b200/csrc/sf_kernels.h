@@ -162,6 +162,24 @@ int siglip_head(cudaStream_t stream, int dtype, const void* image, int ld_i, con
 int l2norm_backward(cudaStream_t stream, int dtype, const void* x, int ldx, const void* dxhat, int ldg, const float* gscale,
                     void* dx, int ldo, int B, int D);
 
+// ---- backward pass (backward.cu, attention.cu): see the kernel comments for the formulas
+int transpose2d(cudaStream_t st, int dtype, const void* in, int ld_in, void* out, int ld_out, int M, int N);
+int colsum(cudaStream_t st, int dtype, const void* x, int ld, int M, int N, float* out);
+int ln_backward(cudaStream_t st, int dtype, const void* x, int ldx, const void* dn, int ldn, float eps, const void* dres, int ldr, void* dx,
+                int ldo, int M, int D);
+int ln_affine_backward(cudaStream_t st, int dtype, const void* x, int ldx, const void* dy, int ldy, const float* gamma, float eps, void* dx,
+                       int ldo, int M, int D, int row_map, int Tn, int Sn, float* dgamma, float* dbeta);
+int gelu_backward(cudaStream_t st, int dtype, void* a_h, void* dh_dpre, long n, int act);
+int gate_backward(cudaStream_t st, int dtype, const void* dx, const void* y, const float* gate, void* dy, long n, float* dgate);
+int wfold_finish(cudaStream_t st, int dtype, const void* G, int ldg, const void* Wp, int ldw, const float* gamma, const float* beta,
+                 const float* db, void* dW, int out_dtype, int ldo, int O, int I, float* dgamma, float* dbeta);
+int embed_table_grad(cudaStream_t st, int dtype, const void* dx, int ld, int B, int Tn, int Sn, int D, int mode, const int* tidx, float* out);
+int rowperm(cudaStream_t st, const void* in, void* out, long M, int row_bytes, int row_map, int Tn, int Sn);
+int attention_backward(cudaStream_t stream, int dtype, int mode, const void* qkv, int ld_qkv, const void* out, int ld_o, const void* dout,
+                       int ld_do, void* dqkv, int ld_dq, int groups, int heads, int L, int T_inner, int causal, float scale);
+int pool_attention_backward(cudaStream_t stream, int dtype, const void* kv, int ld_kv, const float* q, const void* dout, int ld_do,
+                            void* dkv, int ld_dkv, float* dq, int frames, int heads, int S);
+
 // out = cast(in)  (weight / bias packing helpers; n elements)
 int cast(cudaStream_t stream, int src_dtype, const void* src, int dst_dtype, void* dst, size_t n);
 

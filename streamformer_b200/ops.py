@@ -166,3 +166,116 @@ def pool_probe(tokens: torch.Tensor, u: torch.Tensor, wv: torch.Tensor, bv: torc
                                       wv.data_ptr(), bv.data_ptr(), out.data_ptr(), out.stride(0), frames, heads, S),
             "sf_op_pool_probe")
     return out
+
+
+# ------------------------------------------------------------------------------------- backward-pass ops
+def transpose(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[M, N] -> [N, Mpad] (Mpad = M rounded up to 8, padding zeroed): the wgrad operand layout."""
+    _req(x, out)
+    M, Nn = x.shape
+    Mp = (M + 7) // 8 * 8
+    if out is None:
+        out = torch.empty(Nn, Mp, dtype=x.dtype, device=x.device)
+    N.check(N.load().sf_op_transpose(_stream(), sf_dtype(x.dtype), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), M, Nn),
+            "sf_op_transpose")
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    _req(x)
+    M, Nn = x.shape
+    out = torch.empty(Nn, dtype=torch.float32, device=x.device)
+    N.check(N.load().sf_op_colsum(_stream(), sf_dtype(x.dtype), x.data_ptr(), x.stride(0), M, Nn, out.data_ptr()), "sf_op_colsum")
+    return out
+
+
+def ln_backward(x: torch.Tensor, dn: torch.Tensor, eps: float, dres: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, dn, dres, out)
+    M, D = x.shape
+    if out is None:
+        out = torch.empty(M, D, dtype=x.dtype, device=x.device)
+    N.check(N.load().sf_op_ln_backward(_stream(), sf_dtype(x.dtype), x.data_ptr(), x.stride(0), dn.data_ptr(), dn.stride(0), eps,
+                                       _p(dres), dres.stride(0) if dres is not None else 0, out.data_ptr(), out.stride(0), M, D),
+            "sf_op_ln_backward")
+    return out
+
+
+def ln_affine_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                       row_map: int = 0, T: int = 1, S: int = 1) -> torch.Tensor:
+    _req(x, dy, gamma, dgamma, dbeta)
+    assert gamma.dtype == torch.float32 and dgamma.dtype == torch.float32 and dbeta.dtype == torch.float32
+    M, D = x.shape
+    out = torch.empty(M, D, dtype=x.dtype, device=x.device)
+    N.check(N.load().sf_op_ln_affine_backward(_stream(), sf_dtype(x.dtype), x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0),
+                                              gamma.data_ptr(), eps, out.data_ptr(), out.stride(0), M, D, row_map, T, S,
+                                              dgamma.data_ptr(), dbeta.data_ptr()), "sf_op_ln_affine_backward")
+    return out
+
+
+def gelu_backward_(a_h: torch.Tensor, dh_dpre: torch.Tensor, act: int = N.SF_ACT_GELU) -> None:
+    """In place: a -> GELU(a), dh -> dh * GELU'(a)."""
+    _req(a_h, dh_dpre)
+    assert a_h.is_contiguous() and dh_dpre.is_contiguous() and a_h.numel() == dh_dpre.numel()
+    N.check(N.load().sf_op_gelu_backward(_stream(), sf_dtype(a_h.dtype), a_h.data_ptr(), dh_dpre.data_ptr(), a_h.numel(), act),
+            "sf_op_gelu_backward")
+
+
+def gate_backward(dx: torch.Tensor, y: torch.Tensor, gate: torch.Tensor, dgate: torch.Tensor) -> torch.Tensor:
+    _req(dx, y, gate, dgate)
+    assert dx.is_contiguous() and y.is_contiguous() and gate.dtype == torch.float32 and dgate.dtype == torch.float32
+    dy = torch.empty_like(dx)
+    N.check(N.load().sf_op_gate_backward(_stream(), sf_dtype(dx.dtype), dx.data_ptr(), y.data_ptr(), gate.data_ptr(), dy.data_ptr(),
+                                         dx.numel(), dgate.data_ptr()), "sf_op_gate_backward")
+    return dy
+
+
+def wfold_finish(G: torch.Tensor, out_dtype: torch.dtype, Wp: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+                 beta: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None, dgamma: Optional[torch.Tensor] = None,
+                 dbeta: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(G, Wp, gamma, beta, db, dgamma, dbeta)
+    O, I = G.shape
+    dW = torch.empty(O, I, dtype=out_dtype, device=G.device)
+    N.check(N.load().sf_op_wfold_finish(_stream(), sf_dtype(G.dtype), G.data_ptr(), G.stride(0), _p(Wp), Wp.stride(0) if Wp is not None else 0,
+                                        _p(gamma), _p(beta), _p(db), dW.data_ptr(), sf_dtype(out_dtype), I, O, I, _p(dgamma), _p(dbeta)),
+            "sf_op_wfold_finish")
+    return dW
+
+
+def embed_table_grad(dx: torch.Tensor, B: int, T: int, S: int, mode: int, out: torch.Tensor, tidx: Optional[torch.Tensor] = None) -> None:
+    _req(dx, out, tidx)
+    assert out.dtype == torch.float32 and (tidx is None or tidx.dtype == torch.int32)
+    D = dx.shape[-1]
+    N.check(N.load().sf_op_embed_table_grad(_stream(), sf_dtype(dx.dtype), dx.data_ptr(), D, B, T, S, D, mode, _p(tidx), out.data_ptr()),
+            "sf_op_embed_table_grad")
+
+
+def rowperm(x: torch.Tensor, row_map: int, T: int, S: int) -> torch.Tensor:
+    _req(x)
+    assert x.is_contiguous() and x.dim() == 2
+    out = torch.empty_like(x)
+    N.check(N.load().sf_op_rowperm(_stream(), x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1] * x.element_size(), row_map, T, S),
+            "sf_op_rowperm")
+    return out
+
+
+def attention_backward(mode: int, qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, groups: int, heads: int, L: int,
+                       T_inner: int, causal: bool, scale: float, dqkv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mode 0 temporal (groups = sites, L = T), mode 1 spatial (groups = frames, L = S)."""
+    _req(qkv, out, dout, dqkv)
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    N.check(N.load().sf_op_attention_backward(_stream(), sf_dtype(qkv.dtype), mode, qkv.data_ptr(), qkv.stride(0), out.data_ptr(),
+                                              out.stride(0), dout.data_ptr(), dout.stride(0), dqkv.data_ptr(), dqkv.stride(0), groups,
+                                              heads, L, T_inner, int(causal), scale), "sf_op_attention_backward")
+    return dqkv
+
+
+def pool_attention_backward(kv: torch.Tensor, q: torch.Tensor, dout: torch.Tensor, frames: int, heads: int, S: int,
+                            dq: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(kv, q, dout, dq)
+    dkv = torch.empty_like(kv)
+    N.check(N.load().sf_op_pool_attention_backward(_stream(), sf_dtype(kv.dtype), kv.data_ptr(), kv.stride(0), q.data_ptr(), dout.data_ptr(),
+                                                   dout.stride(0), dkv.data_ptr(), dkv.stride(0), _p(dq), frames, heads, S),
+            "sf_op_pool_attention_backward")
+    return dkv
