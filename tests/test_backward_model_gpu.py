@@ -1,0 +1,124 @@
+"""End-to-end gradients of the native backward against torch.autograd through the REAL reference
+classes (staged under baseline/_ref, fp32, on the same GPU) with identical weights and inputs: every parameter's
+gradient of a fixed scalar loss over pooler_output and last_hidden_state.
+
+Tolerance: ours is bf16 end to end (activations, dY operands and weight gradients rounded to bf16 between
+kernels), the reference fp32: per-parameter cosine >= 0.995 and relative RMS <= 6e-2; the loss itself within the
+forward tolerance."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import streamformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference():
+    sys.path.insert(0, ROOT)
+    from baseline import stage_reference as SR
+    if not SR.stage(quiet=True):
+        pytest.skip("reference neither mounted nor staged under baseline/_ref")
+    return SR.import_reference()
+
+
+def _models(layers, lora, seed, dtype=torch.bfloat16, frozen_spatial=False):
+    from streamformer_b200.modeling_timesformer_siglip import StreamformerConfig, TimesformerMultiTaskingModelSigLIP
+    RefConfig, RefModel = _reference()
+    ocfg = O.OracleConfig(num_hidden_layers=layers, add_lora_spatial=lora)
+    w = O.make_weights(ocfg, seed=seed, style="stress")
+    kw = dict(num_hidden_layers=layers, enable_causal_temporal=True, add_lora_spatial=lora)
+    ours = TimesformerMultiTaskingModelSigLIP(StreamformerConfig(**kw))
+    ref = RefModel(RefConfig(**kw))
+    for m in (ours, ref):
+        sd = {k: torch.from_numpy(np.asarray(v)) for k, v in w.items() if k in m.state_dict()}
+        m.load_state_dict(sd, strict=False)
+    ours = ours.to("cuda", dtype).train()
+    ref = ref.to("cuda", torch.float32).train()
+    if frozen_spatial:
+        ours.frozen_spatial()
+        ref.frozen_spatial()
+    return ocfg, ours, ref
+
+
+def _loss(out, w_pool, w_tok):
+    return (out.pooler_output.float() * w_pool).sum() + (out.last_hidden_state.float() * w_tok).sum()
+
+
+def _compare(ours, ref, px, seed, min_cos=0.995, max_rel=6e-2):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B, T = px.shape[:2]
+    w_pool = torch.randn(B, T, 768, generator=g).cuda() * 0.1
+    w_tok = torch.randn(B, T, px.shape[-1] // 16 * (px.shape[-2] // 16), 768, generator=g).cuda() * 0.01
+    lo = _loss(ours(px), w_pool, w_tok)
+    lo.backward()
+    lr = _loss(ref(px.float()), w_pool, w_tok)
+    lr.backward()
+    assert abs(float(lo) - float(lr)) <= 3e-2 * max(1.0, abs(float(lr))), (float(lo), float(lr))
+    refp = dict(ref.named_parameters())
+    worst = []
+    for name, p in ours.named_parameters():
+        rp = refp[name]
+        if not rp.requires_grad:
+            assert p.grad is None or float(p.grad.abs().sum()) == 0.0, f"{name}: frozen parameter received a gradient"
+            continue
+        assert rp.grad is not None, name
+        assert p.grad is not None, f"{name}: no gradient"
+        a, b = p.grad.float().flatten(), rp.grad.float().flatten()
+        nb = float(b.norm())
+        if nb < 1e-8:
+            assert float(a.norm()) < 1e-4, name
+            continue
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        rel = float((a - b).norm() / b.norm())
+        worst.append((cos, rel, name))
+        assert cos >= min_cos and rel <= max_rel, f"{name}: cosine {cos:.5f}, rel {rel:.4g}"
+    return worst
+
+
+def test_gradients_match_reference_autograd_2_layers():
+    ocfg, ours, ref = _models(2, False, 61)
+    px = torch.from_numpy(O.make_pixels(2, 4, ocfg, seed=61)).cuda()
+    worst = _compare(ours, ref, px, 61)
+    assert len(worst) > 60
+
+
+def test_gradients_with_lora_and_frozen_spatial():
+    """The reference's fine-tuning recipe (…siglip.py:1271-1297): LoRA on the spatial attention, base spatial weights frozen."""
+    ocfg, ours, ref = _models(2, True, 62, frozen_spatial=True)
+    px = torch.from_numpy(O.make_pixels(1, 16, ocfg, seed=62)).cuda()
+    _compare(ours, ref, px, 62)
+    assert ours.encoder.layer[0].attention.attention.qkv.weight.grad is None
+    assert ours.encoder.layer[0].attention.attention.qkv_lora_b.weight.grad is not None
+
+
+def test_fp32_master_parameters_receive_fp32_gradients():
+    ocfg, ours, ref = _models(1, False, 63, dtype=torch.float32)
+    px = torch.from_numpy(O.make_pixels(1, 3, ocfg, seed=63)).cuda()
+    _compare(ours, ref, px, 63)
+    assert all(p.grad.dtype == torch.float32 for p in ours.parameters() if p.grad is not None)
+
+
+def test_optimizer_step_is_picked_up_and_loss_decreases():
+    """A few SGD steps on the classification head's loss (forward -> gather -> head -> backward -> step): the
+    engine re-binds after every step and the loss goes down."""
+    from streamformer_b200.heads import TimesformerVideoClassificationHead
+    ocfg, ours, _ = _models(1, False, 64)
+    px = torch.from_numpy(O.make_pixels(4, 4, ocfg, seed=64)).cuda()
+    head = TimesformerVideoClassificationHead().cuda()
+    emb = torch.nn.functional.normalize(torch.randn(10, 768, device="cuda"), dim=-1)
+    head.set_label_embeddings(emb.bfloat16())
+    labels = torch.tensor([1, 3, 5, 7], device="cuda")
+    opt = torch.optim.SGD(list(ours.parameters()) + list(head.parameters()), lr=2e-2)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = head(ours(px), {"label": labels})
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
