@@ -326,6 +326,61 @@ def bench_forward(torch, dist, N, args, dev, dtype, peaks, name, B, T, world, wa
     return res
 
 
+def bench_train_step(torch, dist, N, args, dev, dtype, peaks, B, T, world, warm, reps):
+    """BASELINE configs[3] as a real pre-train step: forward -> all_gather(last-frame pooler_output, labels) ->
+    classification head (SigLIP sigmoid loss over the global batch) -> native backward through the encoder ->
+    (N > 1) all-reduce of the flattened gradients.  No optimizer update in the timed region (the reference's
+    optimizer is DeepSpeed's, outside the path); weights therefore stay bound."""
+    from streamformer_b200.heads import TimesformerVideoClassificationHead, siglip_head
+    model = make_model(torch, args.layers, dev, dtype).train()
+    head = TimesformerVideoClassificationHead().to(dev)
+    torch.manual_seed(1)
+    head.set_label_embeddings(torch.nn.functional.normalize(torch.randn(400, D, device=dev), dim=-1).to(dtype))
+    xs = [torch.randn(B, T, 3, 224, 224, device=dev, dtype=dtype) for _ in range(2)]
+    labels = torch.randint(0, 400, (B,), device=dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def fn(i):
+        for p in params:
+            p.grad = None
+        out = model(xs[i % 2])
+        feats = out.pooler_output[:, -1, :]
+        if world > 1:
+            # the loss needs the global batch: gather features and labels; each rank back-propagates the gradient
+            # of ITS rows of the global loss
+            all_f = torch.empty(world * B, D, device=dev, dtype=dtype)
+            all_l = torch.empty(world * B, dtype=labels.dtype, device=dev)
+            dist.all_gather_into_tensor(all_f, feats.detach().contiguous())
+            dist.all_gather_into_tensor(all_l, labels)
+        loss, _ = siglip_head(feats, head.label_embeddings, head.logit_scale, head.logit_bias, targets=labels,
+                              loss_div=float(world * B), want_logits=False)
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        return loss
+
+    if world > 1:
+        dist.barrier()
+    ts = timed_steps(torch, fn, warm, reps)
+    t = torch.tensor([sum(ts)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / reps
+    fl = 3.0 * flops_per_clip(T, args.layers) * B      # forward + 2x for dgrad / wgrad (recompute not counted)
+    res = {"workload": f"configs[3]: pre-train step, {B} clips/GPU x {world} GPU(s) (global B={B * world}), T={T}: forward + gather + "
+                       "classification-head loss + native backward" + (" + gradient all-reduce" if world > 1 else "") + "; no optimizer update",
+           "global_batch": world * B, "ms_per_step": ms, "frames_per_s": world * B * T / ms * 1e3,
+           "backward_included": True,
+           "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peaks["burst"], "unit": "TFLOP/s",
+                        "frac": fl / (ms * 1e-3) / 1e12 / peaks["burst"],
+                        "note": "3 x algorithmic forward FLOPs (forward, dgrad, wgrad; the layer-wise recompute is extra, executed work) / step time"},
+           "mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30}
+    del model, xs
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -497,6 +552,7 @@ def run_ours(args):
         configs["cfg4_shard"] = bench_forward(torch, dist, N, args, dev, dtype, peaks,
                                               f"configs[3]: batch-sharded forward, 32 clips/GPU x {world} GPU(s) (global B={32 * world}), T=16, "
                                               "forward + all_gather(pooler_output); backward not included in this line", 32, 16, world, 2, 6)
+        configs["cfg4_train_step"] = bench_train_step(torch, dist, N, args, dev, dtype, peaks, 32, 16, world, 1, 3)
         if world == 1:
             configs["cfg5_long_clip"] = bench_forward(torch, dist, N, args, dev, dtype, peaks,
                                                       "configs[4]: long clip B=2 T=128 224x224 bf16, 1 GPU", 2, 128, 1, 3, 10)
