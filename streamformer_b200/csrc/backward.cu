@@ -50,58 +50,74 @@ int done(const char* what) {
 }
 
 // ------------------------------------------------------------------------------- transpose
-// out[n, m] = in[m, n] for m < M (zeros for M <= m < Mpad).  64 x 64 tiles through shared memory, 16-byte
-// global accesses on both sides; the padded row stride keeps the 16-byte reads of the transposed tile
-// conflict-free (row stride 144 B = 36 words: eight rows land on eight distinct bank groups).
+// out[n, m] = in[m, n] for m < M (zeros for M <= m < Mpad).  64 x 64 tiles through shared memory as 32-bit words
+// holding (in[m][n], in[m+1][n]) — two consecutive m of one column, i.e. one word of the transposed row: a thread
+// reads the same 16-byte chunk of rows m and m+1, interleaves them (PRMT) and stores eight words; the transposed
+// rows are read back as words and leave as 16-byte stores.  Row stride 33 words: the word stores see a 2-way bank
+// conflict, the word loads none.
 __global__ void __launch_bounds__(256) transpose_kernel(const uint16_t* __restrict__ in, long ld_in, uint16_t* __restrict__ out,
                                                         long ld_out, int M, int N, int Mpad) {
-  __shared__ __align__(16) uint16_t tile[64][72];
+  __shared__ uint32_t tile[64][33];
   griddep_wait();
   griddep_launch_dependents();
   const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-  for (int i = threadIdx.x; i < 512; i += 256) {
-    const int r = i >> 3, c8 = i & 7;
-    const int m = m0 + r, n = n0 + c8 * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (m < M && n < N) v = *reinterpret_cast<const uint4*>(in + m * ld_in + n);     // N % 8 == 0
-    const uint16_t* e = reinterpret_cast<const uint16_t*>(&v);
+  {
+    const int mp = threadIdx.x >> 3, c8 = threadIdx.x & 7;     // row pair, 8-column chunk
+    const int m = m0 + 2 * mp, n = n0 + c8 * 8;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
+    if (n < N) {                                               // N % 8 == 0: whole chunks
+      if (m < M) a = *reinterpret_cast<const uint4*>(in + m * ld_in + n);
+      if (m + 1 < M) b = *reinterpret_cast<const uint4*>(in + (m + 1) * ld_in + n);
+    }
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) tile[c8 * 8 + j][r] = e[j];
+    for (int j = 0; j < 4; ++j) {
+      tile[c8 * 8 + 2 * j][mp] = __byte_perm(aw[j], bw[j], 0x5410);       // (a.lo, b.lo): column n + 2j
+      tile[c8 * 8 + 2 * j + 1][mp] = __byte_perm(aw[j], bw[j], 0x7632);   // (a.hi, b.hi): column n + 2j + 1
+    }
   }
   __syncthreads();
+#pragma unroll
   for (int i = threadIdx.x; i < 512; i += 256) {
-    const int r = i >> 3, c8 = i & 7;           // r: row of the transposed tile (a column n of the input)
-    const int n = n0 + r, m = m0 + c8 * 8;
-    if (n < N && m < Mpad) *reinterpret_cast<uint4*>(out + n * ld_out + m) = *reinterpret_cast<const uint4*>(&tile[r][c8 * 8]);
+    const int r = i >> 3, q = i & 7;            // r: transposed row (input column), q: group of 8 m values
+    const int n = n0 + r, m = m0 + q * 8;
+    if (n < N && m < Mpad) {
+      uint4 v;
+      v.x = tile[r][q * 4]; v.y = tile[r][q * 4 + 1]; v.z = tile[r][q * 4 + 2]; v.w = tile[r][q * 4 + 3];
+      *reinterpret_cast<uint4*>(out + n * ld_out + m) = v;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------- column sums
+// out[n] += sum over this CTA's row range; a thread owns one 16-byte chunk (8 columns) and every 8th row of the
+// range, so a warp reads 4 rows x 128 contiguous bytes per step.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ld, int M, int N, float* __restrict__ out) {
-  __shared__ float red[8][64];
+  __shared__ float red[8][256 + 8];
   griddep_wait();
   griddep_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 64 + 2 * lane;
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;     // column chunk (of 32 per CTA), row lane
+  const int n = blockIdx.x * 256 + cl * 8;
   const long rows_per = (M + gridDim.y - 1) / gridDim.y;
   const long r0 = rows_per * blockIdx.y, r1 = (r0 + rows_per < M) ? r0 + rows_per : M;
-  float a0 = 0.f, a1 = 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (n < N) {
-    for (long m = r0 + warp; m < r1; m += 8) {
-      const float2 v = Pack2<T>::unpack(*reinterpret_cast<const uint32_t*>(x + m * ld + n));
-      a0 += v.x; a1 += v.y;
+    for (long m = r0 + rl; m < r1; m += 8) {
+      float f[8];
+      unpack8b<T>(*reinterpret_cast<const uint4*>(x + m * ld + n), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
   }
-  red[warp][2 * lane] = a0; red[warp][2 * lane + 1] = a1;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    const int col = blockIdx.x * 64 + threadIdx.x;
-    if (col < N) atomicAdd(out + col, s);
-  }
+  for (int j = 0; j < 8; ++j) red[rl][cl * 8 + j] = acc[j];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < N) atomicAdd(out + col, s);
 }
 
 // ------------------------------------------------------------------------------- LayerNorm backward
@@ -330,7 +346,7 @@ __global__ void __launch_bounds__(256) wfold_finish_kernel(const T* __restrict__
   griddep_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;       // column
   if (i >= I) return;
-  const long rows_per = (O + gridDim.y - 1) / gridDim.y;
+  const long rows_per = 16;                                  // gridDim.y = ceil(O / 16): enough CTAs for weight-sized work
   const long o0 = rows_per * blockIdx.y, o1 = (o0 + rows_per < O) ? o0 + rows_per : O;
   const float gm = gamma ? gamma[i] : 1.f, bt = beta ? beta[i] : 0.f;
   const float inv = (gamma && fabsf(gm) > 1e-20f) ? 1.0f / gm : 0.f;
@@ -422,13 +438,15 @@ int transpose2d(cudaStream_t st, int dtype, const void* in, int ld_in, void* out
 int colsum(cudaStream_t st, int dtype, const void* x, int ld, int M, int N, float* out) {
   if (N <= 0) return 0;
   if (!act_dtype_ok(dtype, "colsum")) return -1;
-  if ((N % 2) || (ld % 2)) { set_error("colsum: N and ld must be even"); return -1; }
+  if ((N % 8) || (ld % 8)) { set_error("colsum: N and ld must be multiples of 8"); return -1; }
   cudaMemsetAsync(out, 0, static_cast<size_t>(N) * sizeof(float), st);
   if (M <= 0) return 0;
-  int parts = (M + 1023) / 1024;
-  if (parts > 128) parts = 128;
+  const int col_blocks = (N + 255) / 256;
+  int parts = (4 * num_sms() + col_blocks - 1) / col_blocks;        // ~4 CTAs per SM in total
+  if (parts > (M + 31) / 32) parts = (M + 31) / 32;
+  if (parts < 1) parts = 1;
   ProfScope ps(st, kProfOther, 0.0, 2.0 * M * N);
-  LaunchCfg lc(dim3(static_cast<unsigned>((N + 63) / 64), static_cast<unsigned>(parts)), dim3(256), 0, st);
+  LaunchCfg lc(dim3(static_cast<unsigned>(col_blocks), static_cast<unsigned>(parts)), dim3(256), 0, st);
   if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, colsum_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(x), static_cast<long>(ld), M, N, out);
   else cudaLaunchKernelEx(&lc.cfg, colsum_kernel<__half>, reinterpret_cast<const __half*>(x), static_cast<long>(ld), M, N, out);
   return done("colsum");
@@ -512,7 +530,7 @@ int gate_backward(cudaStream_t st, int dtype, const void* dx, const void* y, con
 template <typename T>
 static int launch_wfold(cudaStream_t st, const void* G, int ldg, const void* Wp, int ldw, const float* gamma, const float* beta, const float* db,
                         void* dW, int out_dtype, int ldo, int O, int I, float* dgamma, float* dbeta) {
-  int parts = (O + 255) / 256;
+  const int parts = (O + 15) / 16;
   LaunchCfg lc(dim3(static_cast<unsigned>((I + 255) / 256), static_cast<unsigned>(parts)), dim3(256), 0, st);
 #define SF_ARGS(TO) reinterpret_cast<const T*>(G), static_cast<long>(ldg), reinterpret_cast<const T*>(Wp), static_cast<long>(ldw), gamma, beta, db, \
                     reinterpret_cast<TO*>(dW), static_cast<long>(ldo), O, I, dgamma, dbeta
