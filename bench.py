@@ -407,6 +407,7 @@ def run_ours(args):
     S = PATCHES
     NBUF = 4  # rotate inputs: 4 x 38.5 MB (bf16) > L2, and the per-step working set (~0.7 GB) >> 126 MB L2
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    torch.manual_seed(4321 + rank)          # the ranks work on DIFFERENT clips (make_model seeded every rank identically)
     # e2e inputs: uint8 frames as a video decoder hands them over ([B,T,H,W,3]); the loader's
     # ClipToTensor + Normalize(0.5, 0.5) runs inside the patch-embedding front end on the GPU
     host_u8 = [torch.randint(0, 256, (B, T, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]

@@ -36,42 +36,55 @@ _HEAD_MATS = ["head_kv", "head_out", "head_fc1", "head_fc2"]
 
 class _TrainPack:
     """Packed matrices of the bound context as torch tensors (what the forward kernels consume: LayerNorm gamma
-    folded in, LoRA merged) plus their transposes, the B operands of the dgrad GEMMs."""
+    folded in, LoRA merged) plus their transposes, the B operands of the dgrad GEMMs.  Exported lazily per
+    parameter group, so a stand-alone encoder / head / embedding module exports only what it owns."""
 
     def __init__(self, eng, cfg):
-        self.binds = eng.binds
-        D, I, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
-        P = cfg.patch_size
+        self.eng, self.binds = eng, eng.binds
+        D, I = cfg.hidden_size, cfg.intermediate_size
+        P = cfg.patch_size[0] if isinstance(cfg.patch_size, (tuple, list)) else cfg.patch_size
         Kp = cfg.num_channels * P * P
-        shapes = {"t_qkv": (3 * D, D), "t_out": (D, D), "t_dense": (D, D), "s_qkv": (3 * D, D), "s_out": (D, D), "fc1": (I, D),
-                  "fc2": (D, I), "head_kv": (2 * D, D), "head_out": (D, D), "head_fc1": (I, D), "head_fc2": (D, I), "patch": (D, Kp)}
+        self.shapes = {"t_qkv": (3 * D, D), "t_out": (D, D), "t_dense": (D, D), "s_qkv": (3 * D, D), "s_out": (D, D), "fc1": (I, D),
+                       "fc2": (D, I), "head_kv": (2 * D, D), "head_out": (D, D), "head_fc1": (I, D), "head_fc2": (D, I), "patch": (D, Kp)}
+        self.D = D
+        self._layers: Dict[int, Dict[str, torch.Tensor]] = {}
+        self._head: Optional[Dict[str, torch.Tensor]] = None
+        self._patch: Optional[Dict[str, torch.Tensor]] = None
+        self.unit = torch.ones(D, dtype=torch.float32, device=eng.device)
+        self.zero = torch.zeros(D, dtype=torch.float32, device=eng.device)
+
+    def _export(self, layer, name, d):
+        eng = self.eng
+        rows, cols = self.shapes[name]
         dev, dt = eng.device, eng.dtype
         stream = torch.cuda.current_stream(dev).cuda_stream
-        self.layers: List[Dict[str, torch.Tensor]] = []
+        w = torch.empty(rows, cols, dtype=dt, device=dev)
+        wt = torch.empty(cols, rows, dtype=dt, device=dev)
+        b = torch.empty(rows, dtype=torch.float32, device=dev)
+        for t, nm, tr in ((w, name, 0), (wt, name, 1), (b, name + "_b", 0)):
+            N.check(eng.lib.sf_export_packed(eng.handle, stream, layer, nm.encode(), tr, t.data_ptr(), t.numel() * t.element_size()),
+                    "sf_export_packed")
+        d[name], d[name + "_T"], d[name + "_b"] = w, wt, b
 
-        def export(layer, name):
-            rows, cols = shapes[name]
-            w = torch.empty(rows, cols, dtype=dt, device=dev)
-            wt = torch.empty(cols, rows, dtype=dt, device=dev)
-            b = torch.empty(rows, dtype=torch.float32, device=dev)
-            for t, nm, tr in ((w, name, 0), (wt, name, 1), (b, name + "_b", 0)):
-                N.check(eng.lib.sf_export_packed(eng.handle, stream, layer, nm.encode(), tr, t.data_ptr(), t.numel() * t.element_size()),
-                        "sf_export_packed")
-            return w, wt, b
-
-        for l in range(L):
-            d = {}
+    def layer(self, l: int) -> Dict[str, torch.Tensor]:
+        if l not in self._layers:
+            d: Dict[str, torch.Tensor] = {}
             for name in _LAYER_MATS:
-                d[name], d[name + "_T"], d[name + "_b"] = export(l, name)
-            self.layers.append(d)
-        self.head = {}
-        for name in _HEAD_MATS + ["patch"]:
-            self.head[name], self.head[name + "_T"], self.head[name + "_b"] = export(-1, name)
-        q = torch.empty(D, dtype=torch.float32, device=dev)
-        N.check(eng.lib.sf_export_packed(eng.handle, stream, -1, b"head_q", 0, q.data_ptr(), q.numel() * 4), "sf_export_packed")
-        self.head["head_q"] = q
-        self.unit = torch.ones(D, dtype=torch.float32, device=dev)
-        self.zero = torch.zeros(D, dtype=torch.float32, device=dev)
+                self._export(l, name, d)
+            self._layers[l] = d
+        return self._layers[l]
+
+    def head(self) -> Dict[str, torch.Tensor]:
+        if self._head is None:
+            d: Dict[str, torch.Tensor] = {}
+            for name in _HEAD_MATS:
+                self._export(-1, name, d)
+            q = torch.empty(self.D, dtype=torch.float32, device=self.eng.device)
+            stream = torch.cuda.current_stream(self.eng.device).cuda_stream
+            N.check(self.eng.lib.sf_export_packed(self.eng.handle, stream, -1, b"head_q", 0, q.data_ptr(), q.numel() * 4), "sf_export_packed")
+            d["head_q"] = q
+            self._head = d
+        return self._head
 
 
 def _train_pack(eng, cfg) -> _TrainPack:
@@ -87,11 +100,207 @@ def _wgrad(dY: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
     return ops.gemm(ops.transpose(dY), ops.transpose(X))
 
 
-def _vec(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
-    return t.to(like.dtype).reshape(like.shape)
+class _Bwd:
+    """State of one backward pass: the engine, its training pack, the parameters by reference state-dict name and
+    the gradients collected so far."""
+
+    def __init__(self, root, eng, cfg, names):
+        self.eng, self.cfg, self.names = eng, cfg, names
+        self.tp = _train_pack(eng, cfg)
+        self.params = dict(zip(names, [p for p in root.parameters()]))
+        self.grads: Dict[str, Optional[torch.Tensor]] = {n: None for n in names}
+        self.dt, self.dev = eng.dtype, eng.device
+        self.eps = float(cfg.layer_norm_eps)
+        self.act = N.SF_ACT_GELU if cfg.hidden_act == "gelu" else N.SF_ACT_GELU_TANH
+        self.causal = bool(cfg.enable_causal_temporal)
+        self.D, self.I, self.heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+
+    def wants(self, name):
+        p = self.params.get(name)
+        return p is not None and p.requires_grad
+
+    def f32(self, n):
+        return torch.zeros(n, dtype=torch.float32, device=self.dev)
+
+    def put(self, name, g):
+        if self.wants(name):
+            like = self.params[name]
+            self.grads[name] = g.to(like.dtype).reshape(like.shape)
+
+    def result(self):
+        return tuple(self.grads[n] for n in self.names)
+
+    def lin_grads(self, prefix, dY, X, gamma_name=None, lora=None, packed=None):
+        """Gradients of one nn.Linear (weight [+ LoRA factors], bias, and — when its input LayerNorm is folded into
+        it — that LayerNorm's gamma / beta) from dY [M, O] and its input X [M, I] (the NORMALISED rows when folded;
+        `packed` is then the gamma-scaled matrix the forward used)."""
+        wants, params, grads, dt = self.wants, self.params, self.grads, self.dt
+        wname, bname = prefix + ".weight", prefix + ".bias"
+        need_w = wants(wname) or (lora is not None and any(wants(n) for n in lora))
+        need_ln = gamma_name is not None and (wants(gamma_name + ".weight") or wants(gamma_name + ".bias"))
+        folded = gamma_name is not None
+        db = ops.colsum(dY) if (wants(bname) or need_ln or (need_w and folded)) else None
+        if wants(bname):
+            self.put(bname, db)
+        if not (need_w or need_ln):
+            return
+        G = _wgrad(dY, X)
+        pdt = params[wname].dtype
+        if folded:
+            gm = params[gamma_name + ".weight"].detach().float().contiguous()
+            bt = params[gamma_name + ".bias"].detach().float().contiguous()
+            dg, dbt = self.f32(gm.numel()), self.f32(gm.numel())
+            dW = ops.wfold_finish(G, pdt, packed, gm, bt, db, dg, dbt)
+            self.put(gamma_name + ".weight", dg)
+            self.put(gamma_name + ".bias", dbt)
+        else:
+            dW = ops.wfold_finish(G, pdt)
+        if wants(wname):
+            grads[wname] = dW
+        if lora is not None and all(n in params for n in lora):
+            a_name, b_name = lora                       # W_merged = W + B . A  (…siglip.py:653-654, 749-751)
+            A, Bm = params[a_name].detach(), params[b_name].detach()
+            dWl = dW.to(dt).contiguous()
+            if wants(b_name):                            # dB [O, r] = dW [O, I] . A^T
+                grads[b_name] = ops.gemm(dWl, A.to(dt).contiguous()).to(Bm.dtype)
+            if wants(a_name):                            # dA [r, I] = B^T [r, O] . dW [O, I]
+                grads[a_name] = ops.gemm(ops.transpose(Bm.to(dt).contiguous()), ops.transpose(dWl)).to(A.dtype)
+
+    # ------------------------------------------------------------------ one divided space-time block
+    def layer(self, l, x0, dx, B, T, S):
+        """dx (gradient w.r.t. the layer's output [M, D]) -> gradient w.r.t. its input x0; parameter gradients collected."""
+        lw = self.tp.layer(l)
+        p = f"encoder.layer.{l}."
+        heads, eps, tp = self.heads, self.eps, self.tp
+        F = B * T
+        gate = self.params[p + "temporal_attention_gating"].detach().float().reshape(1).contiguous()
+        # ---- recompute the layer with the LayerNorms un-folded (…siglip.py:934-1004)
+        n_t = ops.layernorm(x0, tp.unit, tp.zero, eps)
+        qkv_t = ops.gemm(n_t, lw["t_qkv"], bias=lw["t_qkv_b"])
+        ctx_t = ops.temporal_attention(qkv_t, B * S, heads, T, self.causal, 0.125)
+        u_t = ops.gemm(ctx_t, lw["t_out"], bias=lw["t_out_b"])
+        y_t = ops.gemm(u_t, lw["t_dense"], bias=lw["t_dense_b"])
+        x1 = ops.gemm(u_t, lw["t_dense"], bias=lw["t_dense_b"], residual=x0, gate=gate)
+        n_s = ops.layernorm(x1, tp.unit, tp.zero, eps)
+        qkv_s = ops.gemm(n_s, lw["s_qkv"], bias=lw["s_qkv_b"])
+        ctx_s = ops.spatial_attention(qkv_s, F, heads, S, 0.125, T_inner=T)
+        x2 = ops.gemm(ctx_s, lw["s_out"], bias=lw["s_out_b"], residual=x1)
+        n_a = ops.layernorm(x2, tp.unit, tp.zero, eps)
+        a1 = ops.gemm(n_a, lw["fc1"], bias=lw["fc1_b"])
+        # ---- MLP
+        dh = ops.gemm(dx, lw["fc2_T"])
+        ops.gelu_backward_(a1, dh, self.act)                  # a1 -> h, dh -> dpre
+        self.lin_grads(p + "output.dense", dx, a1)
+        self.lin_grads(p + "intermediate.dense", dh, n_a, gamma_name=p + "layernorm_after", packed=lw["fc1"])
+        dn = ops.gemm(dh, lw["fc1_T"])
+        del dh, a1, n_a
+        dx2 = ops.ln_backward(x2, dn, eps, dres=dx)
+        # ---- spatial branch
+        self.lin_grads(p + "attention.output.dense", dx2, ctx_s,
+                       lora=(p + "attention.output.dense_lora_a.weight", p + "attention.output.dense_lora_b.weight"))
+        dctx = ops.gemm(dx2, lw["s_out_T"])
+        dqkv = ops.attention_backward(1, qkv_s, ctx_s, dctx, F, heads, S, T, False, 0.125)
+        self.lin_grads(p + "attention.attention.qkv", dqkv, n_s, gamma_name=p + "layernorm_before", packed=lw["s_qkv"],
+                       lora=(p + "attention.attention.qkv_lora_a.weight", p + "attention.attention.qkv_lora_b.weight"))
+        dn = ops.gemm(dqkv, lw["s_qkv_T"])
+        del dqkv, qkv_s, ctx_s, n_s, x2
+        dx1 = ops.ln_backward(x1, dn, eps, dres=dx2)
+        del dx2
+        # ---- temporal branch: x1 = x0 + tanh(g) * temporal_dense(out_proj(attn))   (…siglip.py:937-958)
+        dgate = self.f32(1)
+        dy = ops.gate_backward(dx1, y_t, gate, dgate)
+        self.put(p + "temporal_attention_gating", dgate)
+        self.lin_grads(p + "temporal_dense", dy, u_t)
+        du = ops.gemm(dy, lw["t_dense_T"])
+        self.lin_grads(p + "temporal_attention.output.dense", du, ctx_t)
+        dctx = ops.gemm(du, lw["t_out_T"])
+        dqkv = ops.attention_backward(0, qkv_t, ctx_t, dctx, B * S, heads, T, 1, self.causal, 0.125)
+        self.lin_grads(p + "temporal_attention.attention.qkv", dqkv, n_t, gamma_name=p + "temporal_layernorm", packed=lw["t_qkv"])
+        dn = ops.gemm(dqkv, lw["t_qkv_T"])
+        return ops.ln_backward(x0, dn, eps, dres=dx1)
+
+    # ------------------------------------------------------------------ pooling head (…siglip.py:1141-1154)
+    def head(self, tokens2d, dp, F, S, d_tokens=None):
+        """dp [F, D] (gradient w.r.t. the pooled output) -> gradient w.r.t. the tokens [F*S, D] (added to d_tokens)."""
+        hp = self.tp.head()
+        params, D, heads, eps = self.params, self.D, self.heads, self.eps
+        kv = ops.gemm(tokens2d, hp["head_kv"], bias=hp["head_kv_b"])
+        pc = ops.pool_attention(kv, hp["head_q"], F, heads, S)
+        r = ops.gemm(pc, hp["head_out"], bias=hp["head_out_b"])
+        g_h = params["head.layernorm.weight"].detach().float().contiguous()
+        b_h = params["head.layernorm.bias"].detach().float().contiguous()
+        lnr = ops.layernorm(r, g_h, b_h, eps)
+        a1 = ops.gemm(lnr, hp["head_fc1"], bias=hp["head_fc1_b"])
+        dhh = ops.gemm(dp, hp["head_fc2_T"])
+        ops.gelu_backward_(a1, dhh, self.act)                 # a1 -> hidden, dhh -> dpre
+        self.lin_grads("head.mlp.fc2", dp, a1)
+        self.lin_grads("head.mlp.fc1", dhh, lnr)
+        dlnr = ops.gemm(dhh, hp["head_fc1_T"])
+        dg, dbt = self.f32(D), self.f32(D)
+        dr = ops.ln_affine_backward(r, dlnr, g_h, eps, dg, dbt) + dp          # [frames, D]: parameter-scale glue
+        self.put("head.layernorm.weight", dg)
+        self.put("head.layernorm.bias", dbt)
+        self.lin_grads("head.attention.out_proj", dr, pc)
+        dpc = ops.gemm(dr, hp["head_out_T"])
+        dq = self.f32(D)
+        dkv = ops.pool_attention_backward(kv, hp["head_q"], dpc, F, heads, S, dq)
+        # in_proj = [W_q; W_k; W_v]: K/V rows from the token GEMM, Q rows through the constant probe query
+        # q = (W_q probe + b_q) / 8  (…siglip.py:1141-1148; F.multi_head_attention_forward)
+        wn, bn, pn = "head.attention.in_proj_weight", "head.attention.in_proj_bias", "head.probe"
+        if self.wants(wn) or self.wants(bn) or self.wants(pn):
+            ipw, ipb, probe = params[wn], params[bn], params[pn]
+            dq8 = dq * 0.125
+            pr = probe.detach().float().reshape(D)
+            if self.wants(wn):
+                self.grads[wn] = torch.cat([torch.outer(dq8, pr).to(ipw.dtype), _wgrad(dkv, tokens2d).to(ipw.dtype)], 0)
+            if self.wants(bn):
+                self.grads[bn] = torch.cat([dq8, ops.colsum(dkv)]).to(ipb.dtype)
+            if self.wants(pn):
+                self.grads[pn] = (ipw.detach()[:D].float().t() @ dq8).to(probe.dtype).reshape(probe.shape)
+        return ops.gemm(dkv, hp["head_kv_T"], residual=d_tokens)
+
+    # ------------------------------------------------------------------ embeddings (…siglip.py:413-457)
+    def embeddings(self, dx, pixel_values, pix_dtype, B, T, S, H, W):
+        cfg, D, dev = self.cfg, self.D, self.dev
+        emb = "embeddings."
+        if self.wants(emb + "position_embeddings"):
+            g = torch.zeros(S, D, dtype=torch.float32, device=dev)
+            ops.embed_table_grad(dx, B, T, S, 0, g)
+            self.put(emb + "position_embeddings", g)
+        if self.wants(emb + "time_embeddings"):
+            Fr = self.params[emb + "time_embeddings"].shape[1]
+            if T <= Fr:
+                tidx = torch.arange(T, dtype=torch.int32, device=dev)                 # [:, :T] slice (…siglip.py:436-439)
+            else:                                                                     # nearest map (…siglip.py:441-447)
+                tidx = torch.clamp(torch.floor(torch.arange(T, dtype=torch.float32, device=dev) * (float(Fr) / float(T))), max=Fr - 1).to(torch.int32)
+            g = torch.zeros(Fr, D, dtype=torch.float32, device=dev)
+            ops.embed_table_grad(dx, B, T, S, 1, g, tidx)
+            self.put(emb + "time_embeddings", g)
+        wn, bn = emb + "patch_embeddings.projection.weight", emb + "patch_embeddings.projection.bias"
+        if self.wants(wn) or self.wants(bn):
+            dxp = ops.rowperm(dx, N.SF_ROW_BNT_TO_BTN, T, S) if T > 1 else dx           # rows (b,t,n): the patch GEMM's order
+            if self.wants(bn):
+                self.put(bn, ops.colsum(dxp))
+            if self.wants(wn):
+                if pix_dtype in (N.SF_U8, N.SF_U8_HWC):
+                    raise NotImplementedError("gradient of the patch projection with uint8 inputs: pass float pixels for training")
+                P = cfg.patch_size[0] if isinstance(cfg.patch_size, (tuple, list)) else cfg.patch_size
+                patches = ops.im2col(pixel_values.reshape(B * T, cfg.num_channels, H, W), P, self.dt)
+                self.grads[wn] = ops.wfold_finish(_wgrad(dxp, patches), self.params[wn].dtype).reshape(self.params[wn].shape)
+
+
+def _check_geometry(T, S):
+    if T > 208 or S > 208:
+        raise NotImplementedError(f"backward supports attention groups of up to 208 tokens (T={T}, S={S})")
+
+
+def _names(root, eng):
+    return tuple(eng.prefix + n for n, _ in root.named_parameters())
 
 
 class _EncoderFn(torch.autograd.Function):
+    """TimesformerMultiTaskingModelSigLIP.forward: pixels -> (last_hidden_state, pooler_output)."""
+
     @staticmethod
     def forward(ctx, model, eng, pixel_values, pix_dtype, H, W, names, *params):
         cfg = model.config
@@ -102,8 +311,7 @@ class _EncoderFn(torch.autograd.Function):
         if S != model.embeddings.position_embeddings.shape[1] or H != W:
             raise NotImplementedError("training at a non-default resolution (gradients through the bicubic position-table "
                                       "resampling) is not implemented; run it under torch.no_grad()")
-        if T > 208 or S > 208:
-            raise NotImplementedError(f"backward supports attention groups of up to 208 tokens (T={T}, S={S})")
+        _check_geometry(T, S)
         dev = pixel_values.device
         last_hidden = torch.empty(B, T, S, D, dtype=eng.dtype, device=dev)
         pooled = torch.empty(B, T, D, dtype=eng.dtype, device=dev)
@@ -121,205 +329,35 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_lhs, d_pooled, *_unused):
-        model, eng, names = ctx.model, ctx.eng, ctx.names
-        cfg = model.config
+        model, eng = ctx.model, ctx.eng
         pixel_values, last_hidden, *hs = ctx.saved_tensors
         B, T, S, H, W = ctx.geom
-        D, I, L, heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.num_attention_heads
-        M = B * S * T
-        F = B * T
-        dt = eng.dtype
-        dev = last_hidden.device
-        eps = float(cfg.layer_norm_eps)
-        act = N.SF_ACT_GELU if cfg.hidden_act == "gelu" else N.SF_ACT_GELU_TANH
-        causal = bool(cfg.enable_causal_temporal)
-        tp = _train_pack(eng, cfg)
-        params = dict(zip(names, [p for p in model.parameters()]))
-        grads: Dict[str, Optional[torch.Tensor]] = {n: None for n in names}
-
-        def wants(name):
-            p = params.get(name)
-            return p is not None and p.requires_grad
-
-        def f32(n):
-            return torch.zeros(n, dtype=torch.float32, device=dev)
-
-        def put(name, g):
-            if wants(name):
-                grads[name] = _vec(g, params[name])
-
-        def lin_grads(prefix, dY, X, pack=None, gamma_name=None, lora=None, w_key=None, lw=None):
-            """Gradients of one nn.Linear (weight [+ LoRA factors], bias, and — when its input LayerNorm is folded into
-            it — that LayerNorm's gamma / beta) from dY [M, O] and its input X [M, I] (the NORMALISED rows when folded)."""
-            wname, bname = prefix + ".weight", prefix + ".bias"
-            need_w = wants(wname) or (lora is not None and any(wants(n) for n in lora))
-            need_ln = gamma_name is not None and (wants(gamma_name + ".weight") or wants(gamma_name + ".bias"))
-            db = ops.colsum(dY) if (wants(bname) or need_ln or need_w and gamma_name is not None) else None
-            if wants(bname):
-                put(bname, db)
-            if not (need_w or need_ln):
-                return
-            G = _wgrad(dY, X)
-            pdt = params[wname].dtype
-            if gamma_name is not None:
-                gm = params[gamma_name + ".weight"].detach().float().contiguous()
-                bt = params[gamma_name + ".bias"].detach().float().contiguous()
-                dg, dbt = f32(gm.numel()), f32(gm.numel())
-                dW = ops.wfold_finish(G, pdt, lw[w_key], gm, bt, db, dg, dbt)
-                put(gamma_name + ".weight", dg)
-                put(gamma_name + ".bias", dbt)
-            else:
-                dW = ops.wfold_finish(G, pdt)
-            if wants(wname):
-                grads[wname] = dW
-            if lora is not None and all(n in params for n in lora):
-                a_name, b_name = lora                       # W_merged = W + B . A  (…siglip.py:653-654, 749-751)
-                A, Bm = params[a_name].detach(), params[b_name].detach()
-                dWl = dW.to(dt).contiguous()
-                if wants(b_name):                            # dB [O, r] = dW [O, I] . A^T
-                    grads[b_name] = ops.gemm(dWl, A.to(dt).contiguous()).to(Bm.dtype)
-                if wants(a_name):                            # dA [r, I] = B^T [r, O] . dW [O, I]
-                    grads[a_name] = ops.gemm(ops.transpose(Bm.to(dt).contiguous()), ops.transpose(dWl)).to(A.dtype)
-
-        # ------------------------------------------------------------------ pooling head + post_layernorm
-        lhs2d = last_hidden.reshape(M, D)
-        xL = hs[L].reshape(M, D)
-        d_tokens = d_lhs.to(dt).contiguous().reshape(M, D) if d_lhs is not None else None
-        hp = tp.head
+        bw = _Bwd(model, eng, model.config, ctx.names)
+        D, L = bw.D, model.config.num_hidden_layers
+        M, F = B * S * T, B * T
+        d_tokens = d_lhs.to(bw.dt).contiguous().reshape(M, D) if d_lhs is not None else None
         if d_pooled is not None:
-            dp = d_pooled.to(dt).contiguous().reshape(F, D)
-            kv = ops.gemm(lhs2d, hp["head_kv"], bias=hp["head_kv_b"])
-            pc = ops.pool_attention(kv, hp["head_q"], F, heads, S)
-            r = ops.gemm(pc, hp["head_out"], bias=hp["head_out_b"])
-            g_h = params["head.layernorm.weight"].detach().float().contiguous()
-            b_h = params["head.layernorm.bias"].detach().float().contiguous()
-            lnr = ops.layernorm(r, g_h, b_h, eps)
-            a1 = ops.gemm(lnr, hp["head_fc1"], bias=hp["head_fc1_b"])
-            dhh = ops.gemm(dp, hp["head_fc2_T"])
-            ops.gelu_backward_(a1, dhh, act)                 # a1 -> hidden, dhh -> dpre
-            lin_grads("head.mlp.fc2", dp, a1)
-            lin_grads("head.mlp.fc1", dhh, lnr)
-            dlnr = ops.gemm(dhh, hp["head_fc1_T"])
-            dg, dbt = f32(D), f32(D)
-            dr = ops.ln_affine_backward(r, dlnr, g_h, eps, dg, dbt) + dp          # [frames, D]: parameter-scale glue
-            put("head.layernorm.weight", dg)
-            put("head.layernorm.bias", dbt)
-            lin_grads("head.attention.out_proj", dr, pc)
-            dpc = ops.gemm(dr, hp["head_out_T"])
-            dq = f32(D)
-            dkv = ops.pool_attention_backward(kv, hp["head_q"], dpc, F, heads, S, dq)
-            # in_proj = [W_q; W_k; W_v]: K/V rows from the token GEMM, Q rows through the constant probe query
-            # q = (W_q probe + b_q) / 8  (…siglip.py:1141-1148; F.multi_head_attention_forward)
-            ipw, ipb, probe = params["head.attention.in_proj_weight"], params["head.attention.in_proj_bias"], params["head.probe"]
-            need_ip = wants("head.attention.in_proj_weight") or wants("head.attention.in_proj_bias") or wants("head.probe")
-            if need_ip:
-                dq8 = dq * 0.125
-                Gkv = _wgrad(dkv, lhs2d)
-                dbkv = ops.colsum(dkv)
-                pr = probe.detach().float().reshape(D)
-                if wants("head.attention.in_proj_weight"):
-                    grads["head.attention.in_proj_weight"] = torch.cat([torch.outer(dq8, pr).to(ipw.dtype), Gkv.to(ipw.dtype)], 0)
-                if wants("head.attention.in_proj_bias"):
-                    grads["head.attention.in_proj_bias"] = torch.cat([dq8, dbkv]).to(ipb.dtype)
-                if wants("head.probe"):
-                    grads["head.probe"] = (ipw.detach()[:D].float().t() @ dq8).to(probe.dtype).reshape(probe.shape)
-            d_tokens = ops.gemm(dkv, hp["head_kv_T"], residual=d_tokens)
+            d_tokens = bw.head(last_hidden.reshape(M, D), d_pooled.to(bw.dt).contiguous().reshape(F, D), F, S, d_tokens)
         if d_tokens is None:
-            return (None,) * 7 + tuple(None for _ in names)
-        g_p = params["post_layernorm.weight"].detach().float().contiguous()
-        dg, dbt = f32(D), f32(D)
-        dx = ops.ln_affine_backward(xL, d_tokens, g_p, eps, dg, dbt, N.SF_ROW_BNT_TO_BTN if T > 1 else N.SF_ROW_IDENTITY, T, S)
-        put("post_layernorm.weight", dg)
-        put("post_layernorm.bias", dbt)
-        del d_tokens, lhs2d
-
-        # ------------------------------------------------------------------ layers, last to first
+            return (None,) * 7 + bw.result()
+        g_p = bw.params["post_layernorm.weight"].detach().float().contiguous()
+        dg, dbt = bw.f32(D), bw.f32(D)
+        dx = ops.ln_affine_backward(hs[L].reshape(M, D), d_tokens, g_p, bw.eps, dg, dbt,
+                                    N.SF_ROW_BNT_TO_BTN if T > 1 else N.SF_ROW_IDENTITY, T, S)
+        bw.put("post_layernorm.weight", dg)
+        bw.put("post_layernorm.bias", dbt)
+        del d_tokens
         for l in range(L - 1, -1, -1):
-            lw = tp.layers[l]
-            p = f"encoder.layer.{l}."
-            x0 = hs[l].reshape(M, D)
-            gate = params[p + "temporal_attention_gating"].detach().float().reshape(1).contiguous()
-            # ---- recompute the layer with the LayerNorms un-folded (…siglip.py:934-1004)
-            n_t = ops.layernorm(x0, tp.unit, tp.zero, eps)
-            qkv_t = ops.gemm(n_t, lw["t_qkv"], bias=lw["t_qkv_b"])
-            ctx_t = ops.temporal_attention(qkv_t, B * S, heads, T, causal, 0.125)
-            u_t = ops.gemm(ctx_t, lw["t_out"], bias=lw["t_out_b"])
-            y_t = ops.gemm(u_t, lw["t_dense"], bias=lw["t_dense_b"])
-            x1 = ops.gemm(u_t, lw["t_dense"], bias=lw["t_dense_b"], residual=x0, gate=gate)
-            n_s = ops.layernorm(x1, tp.unit, tp.zero, eps)
-            qkv_s = ops.gemm(n_s, lw["s_qkv"], bias=lw["s_qkv_b"])
-            ctx_s = ops.spatial_attention(qkv_s, F, heads, S, 0.125, T_inner=T)
-            x2 = ops.gemm(ctx_s, lw["s_out"], bias=lw["s_out_b"], residual=x1)
-            n_a = ops.layernorm(x2, tp.unit, tp.zero, eps)
-            a1 = ops.gemm(n_a, lw["fc1"], bias=lw["fc1_b"])
-            # ---- MLP
-            dh = ops.gemm(dx, lw["fc2_T"])
-            ops.gelu_backward_(a1, dh, act)                  # a1 -> h, dh -> dpre
-            lin_grads(p + "output.dense", dx, a1)
-            lin_grads(p + "intermediate.dense", dh, n_a, gamma_name=p + "layernorm_after", w_key="fc1", lw=lw)
-            dn = ops.gemm(dh, lw["fc1_T"])
-            del dh, a1, n_a
-            dx2 = ops.ln_backward(x2, dn, eps, dres=dx)
-            # ---- spatial branch
-            lin_grads(p + "attention.output.dense", dx2, ctx_s,
-                      lora=(p + "attention.output.dense_lora_a.weight", p + "attention.output.dense_lora_b.weight"))
-            dctx = ops.gemm(dx2, lw["s_out_T"])
-            dqkv = ops.attention_backward(1, qkv_s, ctx_s, dctx, F, heads, S, T, False, 0.125)
-            lin_grads(p + "attention.attention.qkv", dqkv, n_s, gamma_name=p + "layernorm_before", w_key="s_qkv", lw=lw,
-                      lora=(p + "attention.attention.qkv_lora_a.weight", p + "attention.attention.qkv_lora_b.weight"))
-            dn = ops.gemm(dqkv, lw["s_qkv_T"])
-            del dqkv, qkv_s, ctx_s, n_s, x2
-            dx1 = ops.ln_backward(x1, dn, eps, dres=dx2)
-            del dx2
-            # ---- temporal branch: x1 = x0 + tanh(g) * temporal_dense(out_proj(attn))   (…siglip.py:937-958)
-            dgate = f32(1)
-            dy = ops.gate_backward(dx1, y_t, gate, dgate)
-            put(p + "temporal_attention_gating", dgate)
-            lin_grads(p + "temporal_dense", dy, u_t)
-            du = ops.gemm(dy, lw["t_dense_T"])
-            lin_grads(p + "temporal_attention.output.dense", du, ctx_t)
-            dctx = ops.gemm(du, lw["t_out_T"])
-            dqkv = ops.attention_backward(0, qkv_t, ctx_t, dctx, B * S, heads, T, 1, causal, 0.125)
-            lin_grads(p + "temporal_attention.attention.qkv", dqkv, n_t, gamma_name=p + "temporal_layernorm", w_key="t_qkv", lw=lw)
-            dn = ops.gemm(dqkv, lw["t_qkv_T"])
-            dx = ops.ln_backward(x0, dn, eps, dres=dx1)
-            del dqkv, qkv_t, ctx_t, u_t, y_t, n_t, x1, dx1, dn, dy, du, dctx
-
-        # ------------------------------------------------------------------ embeddings (…siglip.py:413-457)
-        emb = "embeddings."
-        if wants(emb + "position_embeddings"):
-            g = torch.zeros(S, D, dtype=torch.float32, device=dev)
-            ops.embed_table_grad(dx, B, T, S, 0, g)
-            put(emb + "position_embeddings", g)
-        if wants(emb + "time_embeddings"):
-            Fr = params[emb + "time_embeddings"].shape[1]
-            if T <= Fr:
-                tidx = torch.arange(T, dtype=torch.int32, device=dev)                 # [:, :T] slice (…siglip.py:436-439)
-            else:                                                                     # nearest map (…siglip.py:441-447)
-                tidx = torch.clamp(torch.floor(torch.arange(T, dtype=torch.float32, device=dev) * (float(Fr) / float(T))), max=Fr - 1).to(torch.int32)
-            g = torch.zeros(Fr, D, dtype=torch.float32, device=dev)
-            ops.embed_table_grad(dx, B, T, S, 1, g, tidx)
-            put(emb + "time_embeddings", g)
-        wn, bn = emb + "patch_embeddings.projection.weight", emb + "patch_embeddings.projection.bias"
-        if wants(wn) or wants(bn):
-            dxp = ops.rowperm(dx, N.SF_ROW_BNT_TO_BTN, T, S) if T > 1 else dx           # rows (b,t,n): the patch GEMM's order
-            if wants(bn):
-                put(bn, ops.colsum(dxp))
-            if wants(wn):
-                px = pixel_values if ctx.pix_dtype not in (N.SF_U8, N.SF_U8_HWC) else None
-                if px is None:
-                    raise NotImplementedError("gradient of the patch projection with uint8 inputs: pass float pixels for training")
-                patches = ops.im2col(px.reshape(F, cfg.num_channels, H, W), cfg.patch_size, dt)
-                grads[wn] = ops.wfold_finish(_wgrad(dxp, patches), params[wn].dtype).reshape(params[wn].shape)
-        return (None,) * 7 + tuple(grads[n] for n in names)
+            dx = bw.layer(l, hs[l].reshape(M, D), dx, B, T, S)
+        bw.embeddings(dx, pixel_values, ctx.pix_dtype, B, T, S, H, W)
+        return (None,) * 7 + bw.result()
 
 
 def encoder_forward_with_grad(model, eng, pixel_values, pix_dtype, H, W, output_hidden_states, return_dict):
     """Training-mode ``model(pixel_values)``: same outputs as the inference path, differentiable w.r.t. every
     parameter that requires grad (``last_hidden_state`` and ``pooler_output``; ``hidden_states`` are returned detached)."""
-    named = [(n, p) for n, p in model.named_parameters()]
-    names = tuple(n for n, _ in named)
-    out = _EncoderFn.apply(model, eng, pixel_values, pix_dtype, H, W, names, *[p for _, p in named])
+    names = _names(model, eng)
+    out = _EncoderFn.apply(model, eng, pixel_values, pix_dtype, H, W, names, *list(model.parameters()))
     last_hidden, pooled, hs = out[0], out[1], out[2:]
     out_dtype = model.embeddings.position_embeddings.dtype
     if out_dtype != eng.dtype:
@@ -329,3 +367,112 @@ def encoder_forward_with_grad(model, eng, pixel_values, pix_dtype, H, W, output_
     if not return_dict:
         return tuple(v for v in [last_hidden, hs_t] if v is not None)
     return BaseModelOutputWithPooling(last_hidden_state=last_hidden, pooler_output=pooled, hidden_states=hs_t, attentions=None)
+
+
+# ------------------------------------------------------------------------------------- block-level API
+# The sub-modules downstream code composes on its own (downstream/AR/models/modeling_timesformer_video_classification.py:
+# 42-133 fine-tunes embeddings -> encoder -> its own torch post_layernorm -> pooling head): each is differentiable
+# w.r.t. its input activations and its own parameters.
+class _StackFn(torch.autograd.Function):
+    """TimesformerEncoder.forward (all layers) or one TimesformerLayerSigLIP (layers = [index])."""
+
+    @staticmethod
+    def forward(ctx, root, eng, names, layers, num_frames, x, *params):
+        cfg = root.config
+        B, NT, D = x.shape
+        T = num_frames
+        S = NT // T
+        _check_geometry(T, S)
+        x = x.contiguous()
+        hs = [x] + [torch.empty_like(x) for _ in layers]
+        P = cfg.patch_size[0] if isinstance(cfg.patch_size, (tuple, list)) else cfg.patch_size
+        ws = eng.get_workspace(B, T, P, P * S)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        if len(layers) == cfg.num_hidden_layers and len(layers) > 1:
+            N.check(eng.lib.sf_encoder_forward(eng.handle, stream, x.data_ptr(), B, T, S, None, hs[-1].data_ptr(),
+                                               N.ptr_array([t.data_ptr() for t in hs]), None, ws.data_ptr(), ws.numel()), "sf_encoder_forward")
+        else:
+            for i, l in enumerate(layers):
+                N.check(eng.lib.sf_layer_forward(eng.handle, stream, l, hs[i].data_ptr(), hs[i + 1].data_ptr(), B, T, S, None, None,
+                                                 ws.data_ptr(), ws.numel()), "sf_layer_forward")
+        ctx.root, ctx.eng, ctx.names, ctx.layers, ctx.geom = root, eng, names, layers, (B, T, S)
+        ctx.save_for_backward(*hs)
+        ctx.mark_non_differentiable(*hs[1:-1])
+        return tuple(hs[1:][::-1])            # (final output, ..., first layer's output)
+
+    @staticmethod
+    def backward(ctx, d_out, *_unused):
+        hs = ctx.saved_tensors
+        B, T, S = ctx.geom
+        bw = _Bwd(ctx.root, ctx.eng, ctx.root.config, ctx.names)
+        M = B * S * T
+        dx = d_out.to(bw.dt).contiguous().reshape(M, bw.D)
+        for i in range(len(ctx.layers) - 1, -1, -1):
+            dx = bw.layer(ctx.layers[i], hs[i].reshape(M, bw.D), dx, B, T, S)
+        return (None,) * 5 + (dx.reshape(B, S * T, bw.D),) + bw.result()
+
+
+def stack_forward_with_grad(root, eng, layers, hidden_states, num_frames):
+    """Differentiable layers over ``hidden_states`` [B, N*T, D]: returns the list of layer outputs (last = result)."""
+    names = _names(root, eng)
+    outs = _StackFn.apply(root, eng, names, tuple(layers), num_frames, hidden_states.to(eng.dtype), *list(root.parameters()))
+    return list(outs[::-1])
+
+
+class _EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, root, eng, names, pixel_values, pix_dtype, H, W, *params):
+        cfg = root.config
+        B, T = pixel_values.shape[:2]
+        P = cfg.patch_size[0] if isinstance(cfg.patch_size, (tuple, list)) else cfg.patch_size
+        S = (H // P) * (W // P)
+        x = torch.empty(B, S * T, cfg.hidden_size, dtype=eng.dtype, device=pixel_values.device)
+        ws = eng.get_workspace(B, T, H, W)
+        N.check(eng.lib.sf_embed_forward(eng.handle, torch.cuda.current_stream(x.device).cuda_stream, pixel_values.data_ptr(), pix_dtype,
+                                         B, T, H, W, 0, T, x.data_ptr(), ws.data_ptr(), ws.numel()), "sf_embed_forward")
+        ctx.root, ctx.eng, ctx.names, ctx.pix_dtype, ctx.geom = root, eng, names, pix_dtype, (B, T, S, H, W)
+        ctx.save_for_backward(pixel_values)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        (pixel_values,) = ctx.saved_tensors
+        B, T, S, H, W = ctx.geom
+        bw = _Bwd(ctx.root, ctx.eng, ctx.root.config, ctx.names)
+        bw.embeddings(dx.to(bw.dt).contiguous().reshape(B * S * T, bw.D), pixel_values, ctx.pix_dtype, B, T, S, H, W)
+        return (None,) * 7 + bw.result()
+
+
+def embed_forward_with_grad(root, eng, emb, pixel_values, pix_dtype, H, W):
+    S = (H // emb.patch_embeddings.patch_size[0]) * (W // emb.patch_embeddings.patch_size[1])
+    if S != emb.position_embeddings.shape[1] or H != W:
+        raise NotImplementedError("training at a non-default resolution is not implemented; run it under torch.no_grad()")
+    return _EmbedFn.apply(root, eng, _names(root, eng), pixel_values, pix_dtype, H, W, *list(root.parameters()))
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, root, eng, names, tokens, *params):
+        frames, S, D = tokens.shape
+        tokens = tokens.contiguous()
+        out = torch.empty(frames, D, dtype=eng.dtype, device=tokens.device)
+        cfg = root.config
+        P = cfg.patch_size[0] if isinstance(cfg.patch_size, (tuple, list)) else cfg.patch_size
+        ws = eng.get_workspace(frames, 1, P, P * S)
+        N.check(eng.lib.sf_head_forward(eng.handle, torch.cuda.current_stream(tokens.device).cuda_stream, tokens.data_ptr(), frames, S,
+                                        out.data_ptr(), ws.data_ptr(), ws.numel()), "sf_head_forward")
+        ctx.root, ctx.eng, ctx.names = root, eng, names
+        ctx.save_for_backward(tokens)
+        return out
+
+    @staticmethod
+    def backward(ctx, dp):
+        (tokens,) = ctx.saved_tensors
+        frames, S, D = tokens.shape
+        bw = _Bwd(ctx.root, ctx.eng, ctx.root.config, ctx.names)
+        d_tokens = bw.head(tokens.reshape(frames * S, D), dp.to(bw.dt).contiguous(), frames, S)
+        return (None,) * 3 + (d_tokens.reshape(frames, S, D),) + bw.result()
+
+
+def head_forward_with_grad(root, eng, tokens):
+    return _HeadFn.apply(root, eng, _names(root, eng), tokens.to(eng.dtype), *list(root.parameters()))

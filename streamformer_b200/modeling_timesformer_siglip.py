@@ -312,11 +312,17 @@ def _pixel_format(pixel_values: torch.Tensor, num_channels: int) -> Tuple[torch.
     return pixel_values.contiguous(), sf_dtype(pixel_values.dtype), pixel_values.shape[3], pixel_values.shape[4]
 
 
-def _no_autograd(module: nn.Module, what: str) -> None:
-    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise NotImplementedError(
-            f"{what}: the block-level native entry points are forward-only; differentiate through "
-            "TimesformerMultiTaskingModelSigLIP.forward (which has a native backward), or wrap the call in torch.no_grad()")
+def _needs_grad(module: nn.Module, *inputs) -> bool:
+    """Autograd is wanted when grad mode is on and either a parameter of the module or an input requires grad."""
+    if not torch.is_grad_enabled():
+        return False
+    return any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs) or any(p.requires_grad for p in module.parameters())
+
+
+def _no_autograd(what: str, *flags) -> None:
+    if any(flags):
+        raise NotImplementedError(f"{what}: the differentiable path covers neither the KV cache nor output_attentions; "
+                                  "wrap such calls in torch.no_grad()")
 
 
 # =====================================================================================  parameter holders
@@ -371,12 +377,18 @@ class TimesformerEmbeddingsSigLIP(_NativeRoot, nn.Module):
     def forward(self, pixel_values, return_size=False, past_key_values=None):
         """pixels [B,T,C,H,W] (float, or uint8 planar / interleaved [B,T,H,W,C]) -> [B, N*T, D] in the
         reference's (b, n, t) token order; ``past_key_values`` offsets the time embedding (KV:336-366)."""
-        _no_autograd(self, "TimesformerEmbeddingsSigLIP.forward")
         pixel_values, pix_dtype, H, W = _pixel_format(pixel_values, self.config.num_channels)
-        eng = _root_of(self)._engine(pixel_values.device)
+        root = _root_of(self)
+        eng = root._engine(pixel_values.device)
         B, T = pixel_values.shape[:2]
         eng.ensure_pos_table(self, H, W)
         p = self.patch_embeddings.patch_size
+        if _needs_grad(self):
+            _no_autograd("TimesformerEmbeddingsSigLIP.forward", past_key_values is not None)
+            from .autograd import embed_forward_with_grad
+            x = embed_forward_with_grad(root, eng, self, pixel_values, pix_dtype, H, W)
+            x = x.to(self.position_embeddings.dtype) if self.position_embeddings.dtype != eng.dtype else x
+            return (x, H // p[0], W // p[1]) if return_size else x
         S = (H // p[0]) * (W // p[1])
         x = torch.empty(B, S * T, self.config.hidden_size, dtype=eng.dtype, device=pixel_values.device)
         ws = eng.get_workspace(B, T, H, W)
@@ -512,13 +524,18 @@ class TimesformerLayerSigLIP(_NativeRoot, nn.Module):
         """(…siglip.py:900-1004).  With ``past_key_value`` the temporal K/V of the new frames are appended at
         the cache's current position; the caller advances the cache once per step (``cache.advance(T)``)
         after the LAST layer — all layers of a step share the same position."""
-        _no_autograd(self, "TimesformerLayerSigLIP.forward")
-        eng = _root_of(self)._engine(hidden_states.device)
+        root = _root_of(self)
+        eng = root._engine(hidden_states.device)
         B, NT, D = hidden_states.shape
         if NT % num_frames:
             raise ValueError(f"sequence length {NT} is not a multiple of num_frames={num_frames}")
         S = NT // num_frames
         in_dtype = hidden_states.dtype
+        if _needs_grad(self, hidden_states):
+            _no_autograd("TimesformerLayerSigLIP.forward", past_key_value is not None, output_attentions)
+            from .autograd import stack_forward_with_grad
+            out = stack_forward_with_grad(root, eng, [self.layer_index], hidden_states, num_frames)[-1]
+            return (out.to(in_dtype) if in_dtype != eng.dtype and in_dtype.is_floating_point else out,)
         x = hidden_states.to(eng.dtype).contiguous()
         out = torch.empty_like(x)
         heads = self.config.num_attention_heads
@@ -562,13 +579,22 @@ class TimesformerEncoder(_NativeRoot, nn.Module):
     def forward(self, hidden_states: torch.Tensor, num_frames: int, output_attentions: bool = False,
                 output_hidden_states: bool = False, return_dict: bool = True,
                 past_key_values: Optional[StreamformerKVCache] = None):
-        _no_autograd(self, "TimesformerEncoder.forward")
-        eng = _root_of(self)._engine(hidden_states.device)
+        root = _root_of(self)
+        eng = root._engine(hidden_states.device)
         B, NT, D = hidden_states.shape
         if NT % num_frames:
             raise ValueError(f"sequence length {NT} is not a multiple of num_frames={num_frames}")
         S, L = NT // num_frames, len(self.layer)
         in_dtype = hidden_states.dtype
+        if _needs_grad(self, hidden_states):
+            _no_autograd("TimesformerEncoder.forward", past_key_values is not None, output_attentions)
+            from .autograd import stack_forward_with_grad
+            outs = stack_forward_with_grad(root, eng, list(range(L)), hidden_states, num_frames)
+            cast = (lambda t: t.to(in_dtype)) if in_dtype != eng.dtype and in_dtype.is_floating_point else (lambda t: t)
+            hs_t = tuple([hidden_states] + [cast(o) for o in outs]) if output_hidden_states else None
+            if not return_dict:
+                return tuple(v for v in [cast(outs[-1]), hs_t] if v is not None)
+            return BaseModelOutput(last_hidden_state=cast(outs[-1]), hidden_states=hs_t, attentions=None)
         x = hidden_states.to(eng.dtype).contiguous()
         heads = self.config.num_attention_heads
         hs = [x] + [torch.empty_like(x) for _ in range(L)] if output_hidden_states else None
@@ -616,10 +642,14 @@ class TimesformerSiglipMultiheadAttentionPoolingHead(_NativeRoot, nn.Module):
         self.mlp = SiglipMLP(config)
 
     def forward(self, hidden_state):  # (B*T, N, D) -> (B*T, D)
-        _no_autograd(self, "TimesformerSiglipMultiheadAttentionPoolingHead.forward")
-        eng = _root_of(self)._engine(hidden_state.device)
+        root = _root_of(self)
+        eng = root._engine(hidden_state.device)
         frames, S, D = hidden_state.shape
         in_dtype = hidden_state.dtype
+        if _needs_grad(self, hidden_state):
+            from .autograd import head_forward_with_grad
+            out = head_forward_with_grad(root, eng, hidden_state)
+            return out.to(in_dtype) if in_dtype != eng.dtype and in_dtype.is_floating_point else out
         x = hidden_state.to(eng.dtype).contiguous()
         out = torch.empty(frames, D, dtype=eng.dtype, device=x.device)
         P = eng_patch(self.config)
