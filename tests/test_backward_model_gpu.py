@@ -136,3 +136,55 @@ def test_optimizer_step_is_picked_up_and_loss_decreases():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+
+
+def test_block_level_modules_train_like_the_full_model():
+    """The downstream/AR composition (stand-alone embeddings -> encoder -> torch post_layernorm -> pooling head,
+    …video_classification.py:42-133) back-propagates through the native block-level Functions: its parameter
+    gradients equal the full model's for the same weights and loss (same kernels; only the recompute order and
+    one row-statistics pass differ)."""
+    from torch import nn
+    from streamformer_b200 import modeling_timesformer_siglip as M
+    ocfg, full, _ = _models(2, False, 65)
+    hc = full.config
+
+    class Composed(M.TimesformerPreTrainedModel):
+        def __init__(self, config):
+            super().__init__(config)
+            self.embeddings = M.TimesformerEmbeddingsSigLIP(config)
+            self.encoder = M.TimesformerEncoder(config)
+            self.post_layernorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+            self.head = M.TimesformerSiglipMultiheadAttentionPoolingHead(config)
+            self.post_init()
+
+        def forward(self, px):
+            B, T = px.shape[:2]
+            x = self.embeddings(px)
+            x = self.encoder(x, num_frames=T, return_dict=True)[0]
+            seq = self.post_layernorm(x)                                        # torch LayerNorm of the foreign model
+            seq = seq.view(B, -1, T, seq.size(-1)).permute(0, 2, 1, 3)          # (b,n,t) -> (b,t,n)
+            return self.head(seq.reshape(B * T, -1, seq.size(-1))).view(B, T, -1)
+
+    comp = Composed(hc)
+    comp.load_state_dict(full.state_dict(), strict=False)
+    comp = comp.to("cuda", torch.bfloat16).train()
+    px = torch.from_numpy(O.make_pixels(2, 4, ocfg, seed=65)).cuda()
+    w = torch.randn(2, 4, 768, device="cuda") * 0.1
+    (comp(px).float() * w).sum().backward()
+    (full(px).pooler_output.float() * w).sum().backward()
+    fp = dict(full.named_parameters())
+    checked = 0
+    for name, p in comp.named_parameters():
+        a, b = p.grad.float().flatten(), fp[name].grad.float().flatten()
+        if float(b.norm()) < 1e-8 or a.numel() == 1:
+            continue
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        rel = float((a - b).norm() / b.norm())
+        assert cos >= 0.998 and rel <= 5e-2, f"{name}: cosine {cos:.5f}, rel {rel:.4g}"
+        checked += 1
+    assert checked >= 55
+    # a single stand-alone layer is differentiable w.r.t. its input as well
+    lay = M.TimesformerLayerSigLIP(hc, 0).to("cuda", torch.bfloat16).train()
+    x = torch.randn(1, 196 * 2, 768, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    lay(x, 2)[0].float().sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad.float()).all() and float(x.grad.float().abs().sum()) > 0
