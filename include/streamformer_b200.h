@@ -272,6 +272,8 @@ int sf_op_ln_backward(void* stream, int dtype, const void* x, int ldx, const voi
 int sf_op_ln_affine_backward(void* stream, int dtype, const void* x, int ldx, const void* dy, int ld_dy,
                              const float* gamma, float eps, void* dx, int ld_dx, int M, int D, int row_map, int T, int S,
                              float* dgamma, float* dbeta);
+/* h = GELU(a), out of place (the training forward keeps the pre-activation for the backward) */
+int sf_op_gelu(void* stream, int dtype, const void* a, void* h, long long n, int act);
 /* in place: a -> h = GELU(a), dh -> dpre = dh GELU'(a)   (n elements, multiple of 8; act as sf_act) */
 int sf_op_gelu_backward(void* stream, int dtype, void* a_h, void* dh_dpre, long long n, int act);
 /* dy = tanh(*gate) dx;  *dgate += (1 - tanh^2(*gate)) <dx, y>   (…siglip.py:954-958) */

@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "sf_kv_create", "sf_kv_reset", "sf_kv_destroy", "sf_kv_seq_len", "sf_kv_capacity", "sf_kv_advance", "sf_kv_graph_launches", "sf_forward_stream",
     "sf_embed_forward", "sf_layer_forward", "sf_encoder_forward", "sf_final_norm", "sf_head_forward",
     "sf_op_gemm", "sf_op_layernorm", "sf_op_im2col", "sf_op_temporal_attention", "sf_op_temporal_decode", "sf_op_kv_append",
-    "sf_export_packed", "sf_op_transpose", "sf_op_colsum", "sf_op_ln_backward", "sf_op_ln_affine_backward", "sf_op_gelu_backward",
+    "sf_export_packed", "sf_op_transpose", "sf_op_colsum", "sf_op_ln_backward", "sf_op_ln_affine_backward", "sf_op_gelu", "sf_op_gelu_backward",
     "sf_op_gate_backward", "sf_op_wfold_finish", "sf_op_embed_table_grad", "sf_op_rowperm", "sf_op_attention_backward",
     "sf_op_pool_attention_backward",
     "sf_op_spatial_attention", "sf_op_siglip_head", "sf_op_l2norm_backward", "sf_op_pool_attention", "sf_op_pool_probe", "sf_op_rowstats", "sf_op_gemm_stats_parts",
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
     lib.sf_op_colsum.argtypes = [vp, i, vp, i, i, i, vp]
     lib.sf_op_ln_backward.argtypes = [vp, i, vp, i, vp, i, f, vp, i, vp, i, i, i]
     lib.sf_op_ln_affine_backward.argtypes = [vp, i, vp, i, vp, i, vp, f, vp, i, i, i, i, i, i, vp, vp]
+    lib.sf_op_gelu.argtypes = [vp, i, vp, vp, ll, i]
     lib.sf_op_gelu_backward.argtypes = [vp, i, vp, vp, ll, i]
     lib.sf_op_gate_backward.argtypes = [vp, i, vp, vp, vp, vp, ll, vp]
     lib.sf_op_wfold_finish.argtypes = [vp, i, vp, i, vp, i, vp, vp, vp, vp, i, i, i, i, vp, vp]

@@ -167,26 +167,43 @@ class _Bwd:
                 grads[a_name] = ops.gemm(ops.transpose(Bm.to(dt).contiguous()), ops.transpose(dWl)).to(A.dtype)
 
     # ------------------------------------------------------------------ one divided space-time block
-    def layer(self, l, x0, dx, B, T, S):
-        """dx (gradient w.r.t. the layer's output [M, D]) -> gradient w.r.t. its input x0; parameter gradients collected."""
+    _ACTS = ("n_t", "qkv_t", "ctx_t", "u_t", "y_t", "x1", "n_s", "qkv_s", "ctx_s", "x2", "n_a", "a1")
+
+    def layer_forward(self, l, x0, B, T, S, want_output=False):
+        """The layer with its LayerNorms un-folded (…siglip.py:934-1004): every intermediate the backward needs (the
+        normalised rows are wgrad operands, a1 is the MLP pre-activation).  With want_output also the layer output."""
+        lw, tp, heads, eps = self.tp.layer(l), self.tp, self.heads, self.eps
+        gate = self.params[f"encoder.layer.{l}.temporal_attention_gating"].detach().float().reshape(1).contiguous()
+        a = {}
+        a["n_t"] = ops.layernorm(x0, tp.unit, tp.zero, eps)
+        a["qkv_t"] = ops.gemm(a["n_t"], lw["t_qkv"], bias=lw["t_qkv_b"])
+        a["ctx_t"] = ops.temporal_attention(a["qkv_t"], B * S, heads, T, self.causal, 0.125)
+        a["u_t"] = ops.gemm(a["ctx_t"], lw["t_out"], bias=lw["t_out_b"])
+        a["y_t"] = ops.gemm(a["u_t"], lw["t_dense"], bias=lw["t_dense_b"])
+        a["x1"] = ops.gemm(a["u_t"], lw["t_dense"], bias=lw["t_dense_b"], residual=x0, gate=gate)
+        a["n_s"] = ops.layernorm(a["x1"], tp.unit, tp.zero, eps)
+        a["qkv_s"] = ops.gemm(a["n_s"], lw["s_qkv"], bias=lw["s_qkv_b"])
+        a["ctx_s"] = ops.spatial_attention(a["qkv_s"], B * T, heads, S, 0.125, T_inner=T)
+        a["x2"] = ops.gemm(a["ctx_s"], lw["s_out"], bias=lw["s_out_b"], residual=a["x1"])
+        a["n_a"] = ops.layernorm(a["x2"], tp.unit, tp.zero, eps)
+        a["a1"] = ops.gemm(a["n_a"], lw["fc1"], bias=lw["fc1_b"])
+        out = None
+        if want_output:
+            out = ops.gemm(ops.gelu(a["a1"], self.act), lw["fc2"], bias=lw["fc2_b"], residual=a["x2"])
+        return a, out
+
+    def layer(self, l, x0, dx, B, T, S, acts=None):
+        """dx (gradient w.r.t. the layer's output [M, D]) -> gradient w.r.t. its input x0; parameter gradients collected.
+        acts: the intermediates kept by the forward, or None to recompute them (activation checkpointing by layer)."""
         lw = self.tp.layer(l)
         p = f"encoder.layer.{l}."
-        heads, eps, tp = self.heads, self.eps, self.tp
+        heads, eps = self.heads, self.eps
         F = B * T
         gate = self.params[p + "temporal_attention_gating"].detach().float().reshape(1).contiguous()
-        # ---- recompute the layer with the LayerNorms un-folded (…siglip.py:934-1004)
-        n_t = ops.layernorm(x0, tp.unit, tp.zero, eps)
-        qkv_t = ops.gemm(n_t, lw["t_qkv"], bias=lw["t_qkv_b"])
-        ctx_t = ops.temporal_attention(qkv_t, B * S, heads, T, self.causal, 0.125)
-        u_t = ops.gemm(ctx_t, lw["t_out"], bias=lw["t_out_b"])
-        y_t = ops.gemm(u_t, lw["t_dense"], bias=lw["t_dense_b"])
-        x1 = ops.gemm(u_t, lw["t_dense"], bias=lw["t_dense_b"], residual=x0, gate=gate)
-        n_s = ops.layernorm(x1, tp.unit, tp.zero, eps)
-        qkv_s = ops.gemm(n_s, lw["s_qkv"], bias=lw["s_qkv_b"])
-        ctx_s = ops.spatial_attention(qkv_s, F, heads, S, 0.125, T_inner=T)
-        x2 = ops.gemm(ctx_s, lw["s_out"], bias=lw["s_out_b"], residual=x1)
-        n_a = ops.layernorm(x2, tp.unit, tp.zero, eps)
-        a1 = ops.gemm(n_a, lw["fc1"], bias=lw["fc1_b"])
+        if acts is None:
+            acts, _ = self.layer_forward(l, x0, B, T, S)
+        n_t, qkv_t, ctx_t, u_t, y_t, x1, n_s, qkv_s, ctx_s, x2, n_a, a1 = [acts[k] for k in self._ACTS]
+        del acts
         # ---- MLP
         dh = ops.gemm(dx, lw["fc2_T"])
         ops.gelu_backward_(a1, dh, self.act)                  # a1 -> h, dh -> dpre
@@ -298,6 +315,19 @@ def _names(root, eng):
     return tuple(eng.prefix + n for n, _ in root.named_parameters())
 
 
+def _keep_activations(cfg, M, L, dev) -> bool:
+    """Keep every layer's intermediates for the backward (29 KB per token row and layer: 35 GB at 32 clips per GPU —
+    a B200 has 180 GB) instead of recomputing them, unless config.training_recompute forces one way or memory is short."""
+    mode = str(getattr(cfg, "training_recompute", "auto"))
+    if mode in ("always", "True", "true", "1"):
+        return False
+    if mode in ("never", "False", "false", "0"):
+        return True
+    need = 2 * M * L * (9 * cfg.hidden_size + 6 * cfg.hidden_size + cfg.intermediate_size)
+    free, _total = torch.cuda.mem_get_info(dev)
+    return need < 0.45 * free
+
+
 class _EncoderFn(torch.autograd.Function):
     """TimesformerMultiTaskingModelSigLIP.forward: pixels -> (last_hidden_state, pooler_output)."""
 
@@ -313,28 +343,50 @@ class _EncoderFn(torch.autograd.Function):
                                       "resampling) is not implemented; run it under torch.no_grad()")
         _check_geometry(T, S)
         dev = pixel_values.device
+        M = B * S * T
         last_hidden = torch.empty(B, T, S, D, dtype=eng.dtype, device=dev)
         pooled = torch.empty(B, T, D, dtype=eng.dtype, device=dev)
         hs = [torch.empty(B, S * T, D, dtype=eng.dtype, device=dev) for _ in range(L + 1)]
         ws = eng.get_workspace(B, T, H, W)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        N.check(eng.lib.sf_forward(eng.handle, stream, pixel_values.data_ptr(), pix_dtype, B, T, H, W, last_hidden.data_ptr(),
-                                   pooled.data_ptr(), N.ptr_array([t.data_ptr() for t in hs]), None, ws.data_ptr(), ws.numel()),
-                "sf_forward")
+        keep = _keep_activations(cfg, M, L, dev)
+        acts_flat = []
+        if keep:
+            # training forward with the LayerNorms un-folded, every intermediate kept: no recompute in the backward
+            bw = _Bwd(model, eng, cfg, names)
+            N.check(eng.lib.sf_embed_forward(eng.handle, stream, pixel_values.data_ptr(), pix_dtype, B, T, H, W, 0, T, hs[0].data_ptr(),
+                                             ws.data_ptr(), ws.numel()), "sf_embed_forward")
+            for l in range(L):
+                acts, out = bw.layer_forward(l, hs[l].reshape(M, D), B, T, S, want_output=True)
+                hs[l + 1] = out.reshape(B, S * T, D)
+                acts_flat.extend(acts[k] for k in _Bwd._ACTS)
+            N.check(eng.lib.sf_final_norm(eng.handle, stream, hs[L].data_ptr(), B, T, S, last_hidden.data_ptr()), "sf_final_norm")
+            N.check(eng.lib.sf_head_forward(eng.handle, stream, last_hidden.data_ptr(), B * T, S, pooled.data_ptr(), ws.data_ptr(),
+                                            ws.numel()), "sf_head_forward")
+        else:
+            N.check(eng.lib.sf_forward(eng.handle, stream, pixel_values.data_ptr(), pix_dtype, B, T, H, W, last_hidden.data_ptr(),
+                                       pooled.data_ptr(), N.ptr_array([t.data_ptr() for t in hs]), None, ws.data_ptr(), ws.numel()),
+                    "sf_forward")
         ctx.model, ctx.eng, ctx.names, ctx.pix_dtype = model, eng, names, pix_dtype
         ctx.geom = (B, T, S, H, W)
-        ctx.save_for_backward(pixel_values, last_hidden, *hs)
+        ctx.kept = keep
+        ctx.save_for_backward(pixel_values, last_hidden, *hs, *acts_flat)
         ctx.mark_non_differentiable(*hs)
         return (last_hidden, pooled, *hs)
 
     @staticmethod
     def backward(ctx, d_lhs, d_pooled, *_unused):
         model, eng = ctx.model, ctx.eng
-        pixel_values, last_hidden, *hs = ctx.saved_tensors
+        L = model.config.num_hidden_layers
+        saved = ctx.saved_tensors
+        pixel_values, last_hidden = saved[0], saved[1]
+        hs = saved[2:2 + L + 1]
+        acts_flat = list(saved[2 + L + 1:])
         B, T, S, H, W = ctx.geom
         bw = _Bwd(model, eng, model.config, ctx.names)
-        D, L = bw.D, model.config.num_hidden_layers
+        D = bw.D
         M, F = B * S * T, B * T
+        nact = len(_Bwd._ACTS)
         d_tokens = d_lhs.to(bw.dt).contiguous().reshape(M, D) if d_lhs is not None else None
         if d_pooled is not None:
             d_tokens = bw.head(last_hidden.reshape(M, D), d_pooled.to(bw.dt).contiguous().reshape(F, D), F, S, d_tokens)
@@ -348,7 +400,8 @@ class _EncoderFn(torch.autograd.Function):
         bw.put("post_layernorm.bias", dbt)
         del d_tokens
         for l in range(L - 1, -1, -1):
-            dx = bw.layer(l, hs[l].reshape(M, D), dx, B, T, S)
+            acts = dict(zip(_Bwd._ACTS, acts_flat[l * nact:(l + 1) * nact])) if ctx.kept else None
+            dx = bw.layer(l, hs[l].reshape(M, D), dx, B, T, S, acts)
         bw.embeddings(dx, pixel_values, ctx.pix_dtype, B, T, S, H, W)
         return (None,) * 7 + bw.result()
 

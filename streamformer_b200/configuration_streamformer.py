@@ -33,6 +33,8 @@ class StreamformerConfig(PretrainedConfig):
         compute_dtype="bfloat16",      # used when the parameters are fp32: "bfloat16" | "float16"
         fold_temporal_proj=True,       # pre-multiply temporal_dense . temporal out-proj at bind time
         kv_cache_max_frames=64,        # capacity of an auto-created streaming cache
+        training_recompute="auto",     # backward: "never" keeps every layer's intermediates (35 GB at 32 clips/GPU),
+                                       # "always" recomputes them layer by layer, "auto" decides from free memory
         **kwargs,
     ):
         super().__init__(**kwargs)
@@ -58,3 +60,4 @@ class StreamformerConfig(PretrainedConfig):
         self.compute_dtype = compute_dtype
         self.fold_temporal_proj = fold_temporal_proj
         self.kv_cache_max_frames = kv_cache_max_frames
+        self.training_recompute = training_recompute

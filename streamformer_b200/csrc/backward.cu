@@ -304,6 +304,23 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(T* __restrict__ a_h, T* _
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ a, T* __restrict__ h, long n8, int act) {
+  griddep_wait();
+  griddep_launch_dependents();
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    unpack8b<T>(reinterpret_cast<const uint4*>(a)[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float hh, d;
+      gelu_fwd_bwd(v[j], act, hh, d);
+      v[j] = hh;
+    }
+    reinterpret_cast<uint4*>(h)[i] = pack8b<T>(v);
+  }
+}
+
 // ------------------------------------------------------------------------------- temporal gate
 template <typename T>
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const T* __restrict__ dx, const T* __restrict__ y, const float* __restrict__ gate,
@@ -512,6 +529,20 @@ int gelu_backward(cudaStream_t st, int dtype, void* a_h, void* dh_dpre, long n, 
   if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, gelu_bwd_kernel<__nv_bfloat16>, reinterpret_cast<__nv_bfloat16*>(a_h), reinterpret_cast<__nv_bfloat16*>(dh_dpre), n / 8, act);
   else cudaLaunchKernelEx(&lc.cfg, gelu_bwd_kernel<__half>, reinterpret_cast<__half*>(a_h), reinterpret_cast<__half*>(dh_dpre), n / 8, act);
   return done("gelu_backward");
+}
+
+int gelu_forward(cudaStream_t st, int dtype, const void* a, void* h, long n, int act) {
+  if (n <= 0) return 0;
+  if (!act_dtype_ok(dtype, "gelu_forward")) return -1;
+  if (n % 8) { set_error("gelu_forward: element count must be a multiple of 8"); return -1; }
+  if (act != kActGeluErf && act != kActGeluTanh) { set_error("gelu_forward: unknown activation %d", act); return -1; }
+  long blocks = (n / 8 + 255) / 256;
+  if (blocks > 16L * num_sms()) blocks = 16L * num_sms();
+  ProfScope ps(st, kProfOther, 0.0, 4.0 * n);
+  LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st);
+  if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, gelu_fwd_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<__nv_bfloat16*>(h), n / 8, act);
+  else cudaLaunchKernelEx(&lc.cfg, gelu_fwd_kernel<__half>, reinterpret_cast<const __half*>(a), reinterpret_cast<__half*>(h), n / 8, act);
+  return done("gelu_forward");
 }
 
 int gate_backward(cudaStream_t st, int dtype, const void* dx, const void* y, const float* gate, void* dy, long n, float* dgate) {

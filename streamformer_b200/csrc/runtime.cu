@@ -1354,6 +1354,9 @@ int sf_op_ln_affine_backward(void* stream, int dtype, const void* x, int ldx, co
                              void* dx, int ld_dx, int M, int D, int row_map, int T, int S, float* dgamma, float* dbeta) {
   return ln_affine_backward(static_cast<cudaStream_t>(stream), dtype, x, ldx, dy, ld_dy, gamma, eps, dx, ld_dx, M, D, row_map, T, S, dgamma, dbeta);
 }
+int sf_op_gelu(void* stream, int dtype, const void* a, void* h, long long n, int act) {
+  return gelu_forward(static_cast<cudaStream_t>(stream), dtype, a, h, static_cast<long>(n), act);
+}
 int sf_op_gelu_backward(void* stream, int dtype, void* a_h, void* dh_dpre, long long n, int act) {
   return gelu_backward(static_cast<cudaStream_t>(stream), dtype, a_h, dh_dpre, static_cast<long>(n), act);
 }

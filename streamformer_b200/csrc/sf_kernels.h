@@ -169,6 +169,7 @@ int ln_backward(cudaStream_t st, int dtype, const void* x, int ldx, const void* 
                 int ldo, int M, int D);
 int ln_affine_backward(cudaStream_t st, int dtype, const void* x, int ldx, const void* dy, int ldy, const float* gamma, float eps, void* dx,
                        int ldo, int M, int D, int row_map, int Tn, int Sn, float* dgamma, float* dbeta);
+int gelu_forward(cudaStream_t st, int dtype, const void* a, void* h, long n, int act);
 int gelu_backward(cudaStream_t st, int dtype, void* a_h, void* dh_dpre, long n, int act);
 int gate_backward(cudaStream_t st, int dtype, const void* dx, const void* y, const float* gate, void* dy, long n, float* dgate);
 int wfold_finish(cudaStream_t st, int dtype, const void* G, int ldg, const void* Wp, int ldw, const float* gamma, const float* beta,

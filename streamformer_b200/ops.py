@@ -213,6 +213,14 @@ def ln_affine_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, e
     return out
 
 
+def gelu(a: torch.Tensor, act: int = N.SF_ACT_GELU) -> torch.Tensor:
+    _req(a)
+    assert a.is_contiguous()
+    h = torch.empty_like(a)
+    N.check(N.load().sf_op_gelu(_stream(), sf_dtype(a.dtype), a.data_ptr(), h.data_ptr(), a.numel(), act), "sf_op_gelu")
+    return h
+
+
 def gelu_backward_(a_h: torch.Tensor, dh_dpre: torch.Tensor, act: int = N.SF_ACT_GELU) -> None:
     """In place: a -> GELU(a), dh -> dh * GELU'(a)."""
     _req(a_h, dh_dpre)

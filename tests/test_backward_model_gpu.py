@@ -188,3 +188,13 @@ def test_block_level_modules_train_like_the_full_model():
     x = torch.randn(1, 196 * 2, 768, device="cuda", dtype=torch.bfloat16, requires_grad=True)
     lay(x, 2)[0].float().sum().backward()
     assert x.grad is not None and torch.isfinite(x.grad.float()).all() and float(x.grad.float().abs().sum()) > 0
+
+
+@pytest.mark.parametrize("mode", ["always", "never"])
+def test_recompute_and_kept_activation_modes_agree_with_the_reference(mode):
+    """config.training_recompute: "always" = layer-wise recompute in the backward (forward = the fused inference
+    kernels), "never" = training forward with un-folded LayerNorms that keeps every intermediate."""
+    ocfg, ours, ref = _models(2, False, 66)
+    ours.config.training_recompute = mode
+    px = torch.from_numpy(O.make_pixels(1, 5, ocfg, seed=66)).cuda()
+    _compare(ours, ref, px, 66)
