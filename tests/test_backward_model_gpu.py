@@ -60,9 +60,12 @@ def _compare(ours, ref, px, seed, min_cos=0.995, max_rel=6e-2):
     w_tok = torch.randn(B, T, px.shape[-1] // 16 * (px.shape[-2] // 16), 768, generator=g).cuda() * 0.01
     lo = _loss(ours(px), w_pool, w_tok)
     lo.backward()
-    lr = _loss(ref(px.float()), w_pool, w_tok)
+    ro = ref(px.float())
+    lr = _loss(ro, w_pool, w_tok)
     lr.backward()
-    assert abs(float(lo) - float(lr)) <= 3e-2 * max(1.0, abs(float(lr))), (float(lo), float(lr))
+    # the loss is a signed sum of ~10^6 products: compare on the scale of the sum of their magnitudes
+    scale = float((ro.pooler_output.detach() * w_pool).abs().sum() + (ro.last_hidden_state.detach() * w_tok).abs().sum())
+    assert abs(float(lo) - float(lr)) <= 2e-3 * scale, (float(lo), float(lr), scale)
     refp = dict(ref.named_parameters())
     worst, bad = [], []
     for name, p in ours.named_parameters():
