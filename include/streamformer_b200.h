@@ -285,6 +285,15 @@ int sf_op_gate_backward(void* stream, int dtype, const void* dx, const void* y, 
 int sf_op_wfold_finish(void* stream, int dtype, const void* G, int ldg, const void* Wp, int ldw, const float* gamma,
                        const float* beta, const float* db, void* dW, int out_dtype, int ld_dw, int O, int I,
                        float* dgamma, float* dbeta);
+/* weight gradient G = dY^T . X (dY [M, O], X [M, I], row-major activations) on the tcgen05 tensor cores, both operands
+ * read MN-major in place (no transposed copies), token rows split over CTAs: fp32 partials
+ * [sf_op_wgrad_splits(M, O, I)][O][I], to be summed by sf_op_wfold_finish (pass them as `partials` there) */
+int sf_op_wgrad_splits(int M, int O, int I);
+int sf_op_wgrad(void* stream, int dtype, const void* dY, int ldy, const void* X, int ldx, int M, int O, int I, float* partials);
+/* sf_op_wfold_finish with the gradient matrix given as the fp32 split partials of sf_op_wgrad */
+int sf_op_wfold_finish_partials(void* stream, int dtype, const float* partials, int splits, const void* Wp, int ldw,
+                                const float* gamma, const float* beta, const float* db, void* dW, int out_dtype, int ld_dw,
+                                int O, int I, float* dgamma, float* dbeta);
 /* gradients of the embedding tables from dx [B, S*T, D] (rows (b,n,t)): mode 0 position table [S, D],
  * mode 1 time table (out[tidx[t]] += ...), fp32, accumulated */
 int sf_op_embed_table_grad(void* stream, int dtype, const void* dx, int ld, int B, int T, int S, int D, int mode,

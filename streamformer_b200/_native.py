@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "sf_embed_forward", "sf_layer_forward", "sf_encoder_forward", "sf_final_norm", "sf_head_forward",
     "sf_op_gemm", "sf_op_layernorm", "sf_op_im2col", "sf_op_temporal_attention", "sf_op_temporal_decode", "sf_op_kv_append",
     "sf_export_packed", "sf_op_transpose", "sf_op_colsum", "sf_op_ln_backward", "sf_op_ln_affine_backward", "sf_op_gelu", "sf_op_gelu_backward",
-    "sf_op_gate_backward", "sf_op_wfold_finish", "sf_op_embed_table_grad", "sf_op_rowperm", "sf_op_attention_backward",
+    "sf_op_gate_backward", "sf_op_wfold_finish", "sf_op_wgrad", "sf_op_wgrad_splits", "sf_op_wfold_finish_partials", "sf_op_embed_table_grad", "sf_op_rowperm", "sf_op_attention_backward",
     "sf_op_pool_attention_backward",
     "sf_op_spatial_attention", "sf_op_siglip_head", "sf_op_l2norm_backward", "sf_op_pool_attention", "sf_op_pool_probe", "sf_op_rowstats", "sf_op_gemm_stats_parts",
 ]
@@ -124,6 +124,9 @@ def load() -> C.CDLL:
     lib.sf_op_gelu_backward.argtypes = [vp, i, vp, vp, ll, i]
     lib.sf_op_gate_backward.argtypes = [vp, i, vp, vp, vp, vp, ll, vp]
     lib.sf_op_wfold_finish.argtypes = [vp, i, vp, i, vp, i, vp, vp, vp, vp, i, i, i, i, vp, vp]
+    lib.sf_op_wgrad_splits.argtypes = [i, i, i]
+    lib.sf_op_wgrad.argtypes = [vp, i, vp, i, vp, i, i, i, i, vp]
+    lib.sf_op_wfold_finish_partials.argtypes = [vp, i, vp, i, vp, i, vp, vp, vp, vp, i, i, i, i, vp, vp]
     lib.sf_op_embed_table_grad.argtypes = [vp, i, vp, i, i, i, i, i, i, vp, vp]
     lib.sf_op_rowperm.argtypes = [vp, vp, vp, ll, i, i, i, i]
     lib.sf_op_attention_backward.argtypes = [vp, i, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, i, f]

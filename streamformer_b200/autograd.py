@@ -95,9 +95,11 @@ def _train_pack(eng, cfg) -> _TrainPack:
     return tp
 
 
-def _wgrad(dY: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
-    """G[O, I] = dY^T . X  (dY [M, O], X [M, I]) on the tcgen05 GEMM: both operands made M-contiguous first."""
-    return ops.gemm(ops.transpose(dY), ops.transpose(X))
+def _wgrad(dY: torch.Tensor, X: torch.Tensor, out_dtype: torch.dtype, **fold) -> torch.Tensor:
+    """dW [O, I] = dY^T . X  (dY [M, O], X [M, I]): the tcgen05 wgrad kernel reads both activations MN-major in place and
+    leaves fp32 split-K partials; wfold_finish sums them, applies the LayerNorm fold (``fold``: Wp, gamma, beta, db,
+    dgamma, dbeta) and casts to the parameter dtype."""
+    return ops.wfold_finish_partials(ops.wgrad(dY, X), dY.dtype, out_dtype, **fold)
 
 
 class _Bwd:
@@ -144,17 +146,16 @@ class _Bwd:
             self.put(bname, db)
         if not (need_w or need_ln):
             return
-        G = _wgrad(dY, X)
         pdt = params[wname].dtype
         if folded:
             gm = params[gamma_name + ".weight"].detach().float().contiguous()
             bt = params[gamma_name + ".bias"].detach().float().contiguous()
             dg, dbt = self.f32(gm.numel()), self.f32(gm.numel())
-            dW = ops.wfold_finish(G, pdt, packed, gm, bt, db, dg, dbt)
+            dW = _wgrad(dY, X, pdt, Wp=packed, gamma=gm, beta=bt, db=db, dgamma=dg, dbeta=dbt)
             self.put(gamma_name + ".weight", dg)
             self.put(gamma_name + ".bias", dbt)
         else:
-            dW = ops.wfold_finish(G, pdt)
+            dW = _wgrad(dY, X, pdt)
         if wants(wname):
             grads[wname] = dW
         if lora is not None and all(n in params for n in lora):
@@ -269,7 +270,7 @@ class _Bwd:
             dq8 = dq * 0.125
             pr = probe.detach().float().reshape(D)
             if self.wants(wn):
-                self.grads[wn] = torch.cat([torch.outer(dq8, pr).to(ipw.dtype), _wgrad(dkv, tokens2d).to(ipw.dtype)], 0)
+                self.grads[wn] = torch.cat([torch.outer(dq8, pr).to(ipw.dtype), _wgrad(dkv, tokens2d, ipw.dtype)], 0)
             if self.wants(bn):
                 self.grads[bn] = torch.cat([dq8, ops.colsum(dkv)]).to(ipb.dtype)
             if self.wants(pn):
@@ -303,7 +304,7 @@ class _Bwd:
                     raise NotImplementedError("gradient of the patch projection with uint8 inputs: pass float pixels for training")
                 P = cfg.patch_size[0] if isinstance(cfg.patch_size, (tuple, list)) else cfg.patch_size
                 patches = ops.im2col(pixel_values.reshape(B * T, cfg.num_channels, H, W), P, self.dt)
-                self.grads[wn] = ops.wfold_finish(_wgrad(dxp, patches), self.params[wn].dtype).reshape(self.params[wn].shape)
+                self.grads[wn] = _wgrad(dxp, patches, self.params[wn].dtype).reshape(self.params[wn].shape)
 
 
 def _check_geometry(T, S):

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libstreamformer_b200.so")
-SOURCES = ["common.cu", "gemm_tcgen05.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "backward.cu", "runtime.cu"]
+SOURCES = ["common.cu", "gemm_tcgen05.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "backward.cu", "wgrad_tcgen05.cu", "runtime.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

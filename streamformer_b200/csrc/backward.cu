@@ -355,7 +355,8 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const T* __restrict__ dx,
 //   dgamma[i] = sum_o G[o,i] W[o,i],  dbeta[i] = sum_o db'[o] W[o,i]  with W = W' / gamma (the packed, rounded matrix).
 // gamma == nullptr: plain Linear, dW = G.
 template <typename T, typename TO>
-__global__ void __launch_bounds__(256) wfold_finish_kernel(const T* __restrict__ G, long ldg, const T* __restrict__ Wp, long ldw,
+__global__ void __launch_bounds__(256) wfold_finish_kernel(const T* __restrict__ G, const float* __restrict__ Gf, int splits, long ldg,
+                                                           const T* __restrict__ Wp, long ldw,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ db, TO* __restrict__ dW, long ldo, int O, int I,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -369,7 +370,12 @@ __global__ void __launch_bounds__(256) wfold_finish_kernel(const T* __restrict__
   const float inv = (gamma && fabsf(gm) > 1e-20f) ? 1.0f / gm : 0.f;
   float ag = 0.f, ab = 0.f;
   for (long o = o0; o < o1; ++o) {
-    const float g = static_cast<float>(G[o * ldg + i]);
+    float g = 0.f;
+    if (Gf) {                                   // fp32 split-K partials [splits][O][ldg] of the wgrad kernel
+      for (int sp = 0; sp < splits; ++sp) g += Gf[(static_cast<long>(sp) * O + o) * ldg + i];
+    } else {
+      g = static_cast<float>(G[o * ldg + i]);
+    }
     const float dbo = db ? db[o] : 0.f;
     dW[o * ldo + i] = static_cast<TO>(fmaf(g, gm, dbo * bt));
     if (gamma) {
@@ -559,11 +565,11 @@ int gate_backward(cudaStream_t st, int dtype, const void* dx, const void* y, con
 }
 
 template <typename T>
-static int launch_wfold(cudaStream_t st, const void* G, int ldg, const void* Wp, int ldw, const float* gamma, const float* beta, const float* db,
-                        void* dW, int out_dtype, int ldo, int O, int I, float* dgamma, float* dbeta) {
+static int launch_wfold(cudaStream_t st, const void* G, const float* Gf, int splits, int ldg, const void* Wp, int ldw, const float* gamma,
+                        const float* beta, const float* db, void* dW, int out_dtype, int ldo, int O, int I, float* dgamma, float* dbeta) {
   const int parts = (O + 15) / 16;
   LaunchCfg lc(dim3(static_cast<unsigned>((I + 255) / 256), static_cast<unsigned>(parts)), dim3(256), 0, st);
-#define SF_ARGS(TO) reinterpret_cast<const T*>(G), static_cast<long>(ldg), reinterpret_cast<const T*>(Wp), static_cast<long>(ldw), gamma, beta, db, \
+#define SF_ARGS(TO) reinterpret_cast<const T*>(G), Gf, splits, static_cast<long>(ldg), reinterpret_cast<const T*>(Wp), static_cast<long>(ldw), gamma, beta, db, \
                     reinterpret_cast<TO*>(dW), static_cast<long>(ldo), O, I, dgamma, dbeta
   if (out_dtype == kF32) cudaLaunchKernelEx(&lc.cfg, wfold_finish_kernel<T, float>, SF_ARGS(float));
   else if (out_dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, wfold_finish_kernel<T, __nv_bfloat16>, SF_ARGS(__nv_bfloat16));
@@ -572,13 +578,14 @@ static int launch_wfold(cudaStream_t st, const void* G, int ldg, const void* Wp,
   return done("wfold_finish");
 }
 int wfold_finish(cudaStream_t st, int dtype, const void* G, int ldg, const void* Wp, int ldw, const float* gamma, const float* beta,
-                 const float* db, void* dW, int out_dtype, int ldo, int O, int I, float* dgamma, float* dbeta) {
+                 const float* db, void* dW, int out_dtype, int ldo, int O, int I, float* dgamma, float* dbeta, const float* Gf, int splits) {
   if (O <= 0 || I <= 0) return 0;
+  if (!G && !Gf) { set_error("wfold_finish: no gradient matrix"); return -1; }
   if (!act_dtype_ok(dtype, "wfold_finish")) return -1;
   if (gamma && !Wp) { set_error("wfold_finish: the packed matrix is needed for the LayerNorm parameter gradients"); return -1; }
   ProfScope ps(st, kProfOther, 0.0, 6.0 * O * I);
-  return dtype == kBF16 ? launch_wfold<__nv_bfloat16>(st, G, ldg, Wp, ldw, gamma, beta, db, dW, out_dtype, ldo, O, I, dgamma, dbeta)
-                        : launch_wfold<__half>(st, G, ldg, Wp, ldw, gamma, beta, db, dW, out_dtype, ldo, O, I, dgamma, dbeta);
+  return dtype == kBF16 ? launch_wfold<__nv_bfloat16>(st, G, Gf, splits, ldg, Wp, ldw, gamma, beta, db, dW, out_dtype, ldo, O, I, dgamma, dbeta)
+                        : launch_wfold<__half>(st, G, Gf, splits, ldg, Wp, ldw, gamma, beta, db, dW, out_dtype, ldo, O, I, dgamma, dbeta);
 }
 
 int embed_table_grad(cudaStream_t st, int dtype, const void* dx, int ld, int B, int Tn, int Sn, int D, int mode, const int* tidx, float* out) {

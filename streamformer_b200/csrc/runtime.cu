@@ -1367,6 +1367,16 @@ int sf_op_wfold_finish(void* stream, int dtype, const void* G, int ldg, const vo
                        const float* db, void* dW, int out_dtype, int ld_dw, int O, int I, float* dgamma, float* dbeta) {
   return wfold_finish(static_cast<cudaStream_t>(stream), dtype, G, ldg, Wp, ldw, gamma, beta, db, dW, out_dtype, ld_dw, O, I, dgamma, dbeta);
 }
+int sf_op_wgrad_splits(int M, int O, int I) { return wgrad_splits(M, O, I); }
+int sf_op_wgrad(void* stream, int dtype, const void* dY, int ldy, const void* X, int ldx, int M, int O, int I, float* partials) {
+  return wgrad(static_cast<cudaStream_t>(stream), dtype, dY, ldy, X, ldx, M, O, I, partials);
+}
+int sf_op_wfold_finish_partials(void* stream, int dtype, const float* partials, int splits, const void* Wp, int ldw, const float* gamma,
+                                const float* beta, const float* db, void* dW, int out_dtype, int ld_dw, int O, int I, float* dgamma,
+                                float* dbeta) {
+  return wfold_finish(static_cast<cudaStream_t>(stream), dtype, nullptr, I, Wp, ldw, gamma, beta, db, dW, out_dtype, ld_dw, O, I, dgamma,
+                      dbeta, partials, splits);
+}
 int sf_op_embed_table_grad(void* stream, int dtype, const void* dx, int ld, int B, int T, int S, int D, int mode, const int* tidx, float* out) {
   return embed_table_grad(static_cast<cudaStream_t>(stream), dtype, dx, ld, B, T, S, D, mode, tidx, out);
 }

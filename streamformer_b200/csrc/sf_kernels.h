@@ -173,7 +173,12 @@ int gelu_forward(cudaStream_t st, int dtype, const void* a, void* h, long n, int
 int gelu_backward(cudaStream_t st, int dtype, void* a_h, void* dh_dpre, long n, int act);
 int gate_backward(cudaStream_t st, int dtype, const void* dx, const void* y, const float* gate, void* dy, long n, float* dgate);
 int wfold_finish(cudaStream_t st, int dtype, const void* G, int ldg, const void* Wp, int ldw, const float* gamma, const float* beta,
-                 const float* db, void* dW, int out_dtype, int ldo, int O, int I, float* dgamma, float* dbeta);
+                 const float* db, void* dW, int out_dtype, int ldo, int O, int I, float* dgamma, float* dbeta,
+                 const float* Gf = nullptr, int splits = 0);   // Gf: fp32 split-K partials [splits][O][ldg] instead of G
+// G[O, I] = dY^T . X on tcgen05 with MN-major operands straight from the row-major activations (wgrad_tcgen05.cu);
+// partials: fp32 [wgrad_splits(M, O, I)][O][I], summed by wfold_finish
+int wgrad_splits(int M, int O, int I);
+int wgrad(cudaStream_t stream, int dtype, const void* dY, int ldy, const void* X, int ldx, int M, int O, int I, float* partials);
 int embed_table_grad(cudaStream_t st, int dtype, const void* dx, int ld, int B, int Tn, int Sn, int D, int mode, const int* tidx, float* out);
 int rowperm(cudaStream_t st, const void* in, void* out, long M, int row_bytes, int row_map, int Tn, int Sn);
 int attention_backward(cudaStream_t stream, int dtype, int mode, const void* qkv, int ld_qkv, const void* out, int ld_o, const void* dout,

@@ -250,6 +250,31 @@ def wfold_finish(G: torch.Tensor, out_dtype: torch.dtype, Wp: Optional[torch.Ten
     return dW
 
 
+def wgrad(dY: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """fp32 split-K partials [splits, O, I] of G = dY^T . X (tcgen05, MN-major operands read in place)."""
+    _req(dY, X)
+    M, O = dY.shape
+    I = X.shape[1]
+    assert X.shape[0] == M and dY.stride(1) == 1 and X.stride(1) == 1
+    splits = int(N.load().sf_op_wgrad_splits(M, O, I))
+    parts = torch.empty(splits, O, I, dtype=torch.float32, device=dY.device)
+    N.check(N.load().sf_op_wgrad(_stream(), sf_dtype(dY.dtype), dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0), M, O, I,
+                                 parts.data_ptr()), "sf_op_wgrad")
+    return parts
+
+
+def wfold_finish_partials(parts: torch.Tensor, act_dtype: torch.dtype, out_dtype: torch.dtype, Wp: Optional[torch.Tensor] = None,
+                          gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None,
+                          dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(parts, Wp, gamma, beta, db, dgamma, dbeta)
+    splits, O, I = parts.shape
+    dW = torch.empty(O, I, dtype=out_dtype, device=parts.device)
+    N.check(N.load().sf_op_wfold_finish_partials(_stream(), sf_dtype(act_dtype), parts.data_ptr(), splits, _p(Wp),
+                                                 Wp.stride(0) if Wp is not None else 0, _p(gamma), _p(beta), _p(db), dW.data_ptr(),
+                                                 sf_dtype(out_dtype), I, O, I, _p(dgamma), _p(dbeta)), "sf_op_wfold_finish_partials")
+    return dW
+
+
 def embed_table_grad(dx: torch.Tensor, B: int, T: int, S: int, mode: int, out: torch.Tensor, tidx: Optional[torch.Tensor] = None) -> None:
     _req(dx, out, tidx)
     assert out.dtype == torch.float32 and (tidx is None or tidx.dtype == torch.int32)

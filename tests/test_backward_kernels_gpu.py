@@ -45,6 +45,25 @@ def test_wgrad_via_transpose_and_gemm():
     _close(G, dY.float().t() @ X.float(), torch.bfloat16, "wgrad")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,O,I", [(25088, 768, 768), (1571, 2304, 768), (588, 768, 3072), (100, 128, 256), (4100, 1536, 768), (33, 32, 768),
+                                   (6272, 768, 40)])
+def test_wgrad_tcgen05_mn_major(dtype, M, O, I):
+    """G = dY^T . X with both operands read MN-major in place (ragged M / O / I tiles, more splits than row blocks)."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M + O + I)
+    dY = (torch.randn(M, O, generator=g) * 0.1).to(DEV, dtype)
+    X = torch.randn(M, I, generator=g).to(DEV, dtype)
+    parts = ops.wgrad(dY, X)
+    assert parts.dtype == torch.float32 and parts.shape[1:] == (O, I)
+    want = dY.float().t() @ X.float()
+    got = parts.sum(0)
+    err = float((got - want).abs().max())
+    assert err <= 2e-3 * float(want.abs().max()) + 1e-4, f"max err {err:.4g} (ref max {float(want.abs().max()):.4g}, splits {parts.shape[0]})"
+    dW = ops.wfold_finish_partials(parts, dtype, torch.float32)
+    assert float((dW - got).abs().max()) <= 1e-5 * max(1.0, float(got.abs().max()))
+
+
 @pytest.mark.parametrize("M,N", [(25088, 768), (777, 2304), (3, 64)])
 def test_colsum(M, N):
     ops = _ops()
