@@ -85,7 +85,11 @@ uint64_t sf_launch_count(void);
  * (out-proj -> fc1 -> fc2 -> next QKV ...) as one persistent launch with in-kernel row dependencies,
  * 0 one launch per GEMM, -1 the default (SF_GEMM_CHAIN environment variable, off).
  * "stream_graph": 0 serves streaming steps with direct launches, 1 from the captured CUDA graph, -1 the
- * default (SF_STREAM_GRAPH environment variable, on). */
+ * default (SF_STREAM_GRAPH environment variable, on).
+ * "dual_stream": 1 runs a one-shot forward of an even batch as two half batches on two streams (the caller's and
+ * a context-owned one, forked / joined with events) so that one half's kernel fill and drain overlap the other
+ * half's steady state; 0 single stream; -1 the default (SF_DUAL_STREAM environment variable, on).  Profiling
+ * modes, hidden-state / attention outputs, the KV cache and stream capture always use the single-stream schedule. */
 int sf_set_option(const char* name, int value);
 
 /* In-situ profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.

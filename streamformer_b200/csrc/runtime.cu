@@ -171,6 +171,10 @@ struct sf_ctx {
   // loaders: extract_oad_feature.py:42-48, datasets/kinetics_sparse.py:110-118)
   float pix_mean[4] = {0.5f, 0.5f, 0.5f, 0.5f}, pix_std[4] = {0.5f, 0.5f, 0.5f, 0.5f};
   int pos_epoch = 0;           // bumped whenever pos_alt is re-allocated (captured graphs hold its address)
+  // dual-stream forward: the batch runs as two halves on two streams so that one half's kernel fill / drain
+  // overlaps the other half's steady state (see forward_dual)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   std::vector<LayerW> layers;
@@ -502,6 +506,78 @@ int check_groups(const sf_ctx* c, bool embed, int l0, int l1, bool post, bool he
   return 0;
 }
 
+int g_dual_stream_opt = -1;   // sf_set_option("dual_stream", v): -1 environment default (SF_DUAL_STREAM, on), 0 off, 1 on
+bool dual_stream_enabled() {
+  static const bool env_on = [] { const char* e = getenv("SF_DUAL_STREAM"); return !(e && e[0] == '0'); }();
+  return g_dual_stream_opt < 0 ? env_on : g_dual_stream_opt != 0;
+}
+
+// One-shot forward of an even batch as TWO half batches on two streams (the caller's and a context-owned one),
+// launches issued alternately layer by layer.  Clips are independent, so the halves share nothing but
+// the weights.  Every GEMM of a layer depends on the previous kernel of its own half, so a single stream leaves the
+// machine partly idle while each persistent kernel fills (first operand tiles in flight) and drains (last tile's
+// epilogue, SMs without a tile in the last wave) — ~12 us of a 30..100 us kernel; with two independent chains the SMs one
+// half's kernel releases are picked up by the other half's next kernel.
+int forward_dual(sf_ctx* c, cudaStream_t st0, const void* pixels, int pix_dtype, int B, int T, int Hh, int Ww, void* last_hidden,
+                 void* pooler, void* ws, size_t ws_bytes) {
+  const int P = c->cfg.patch_size, D = c->D, C = c->cfg.num_channels;
+  const int S = (Hh / P) * (Ww / P);
+  const int Bh = B / 2;
+  const long Mh = static_cast<long>(Bh) * T * S;
+  if (!c->aux_stream) {
+    SF_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    SF_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    SF_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t sts[2] = {st0, c->aux_stream};
+  SF_CUDA(cudaEventRecord(c->ev_fork, st0));
+  SF_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+  Bump b;
+  b.base = static_cast<uint8_t*>(ws);
+  b.size = ws_bytes;
+  void* x[2];
+  WsPlan w[2];
+  uint8_t* region_end[2];
+  for (int h = 0; h < 2; ++h) {
+    x[h] = b.take(Mh * D * 2);
+    SF_CHECK(carve_layer_ws(c, Mh, b, w[h]));
+    w[h].chain_ctr = nullptr;                     // the chained schedule keeps per-context counter state: single-stream only
+    region_end[h] = static_cast<uint8_t*>(ws) + (b.off < ws_bytes ? b.off : ws_bytes);
+  }
+  if (b.overflow) { set_error("workspace too small"); return SF_ERR_WORKSPACE; }
+  const size_t pix_half = static_cast<size_t>(Bh) * T * C * Hh * Ww * dtype_size(pix_dtype);
+  int parts_d[2];
+  bool qkv_ready[2] = {false, false};
+  for (int h = 0; h < 2; ++h) {
+    SF_CHECK(run_embed(c, sts[h], static_cast<const uint8_t*>(pixels) + h * pix_half, pix_dtype, Bh, T, Hh, Ww, 0, T, x[h], w[h].mlp,
+                       w[h].stats[2]));
+    parts_d[h] = gemm_stats_parts(static_cast<int>(Mh), D);
+  }
+  for (int l = 0; l < c->L; ++l) {
+    const LayerW* next = (l + 1 < c->L) ? &c->layers[l + 1] : nullptr;
+    for (int h = 0; h < 2; ++h) {
+      bool next_done = false;
+      SF_CHECK(run_layer(c, sts[h], l, x[h], x[h], Bh, T, S, nullptr, nullptr, w[h], w[h].stats[2], parts_d[h], w[h].stats[2], nullptr,
+                         qkv_ready[h], next, &next_done, &parts_d[h]));
+      qkv_ready[h] = next_done;
+    }
+  }
+  for (int h = 0; h < 2; ++h) {
+    uint8_t* lh = static_cast<uint8_t*>(last_hidden) + static_cast<size_t>(h) * Mh * D * 2;
+    SF_CHECK(layernorm(sts[h], c->cfg.dtype, x[h], D, c->post_g, c->post_b, c->cfg.layer_norm_eps, lh, D, Mh, D,
+                       T > 1 ? kRowBNTtoBTN : kRowIdentity, T, S));
+    if (pooler) {
+      Bump hb;
+      hb.base = static_cast<uint8_t*>(w[h].qkv);
+      hb.size = region_end[h] - static_cast<uint8_t*>(w[h].qkv);
+      SF_CHECK(run_head(c, sts[h], lh, Bh * T, S, static_cast<uint8_t*>(pooler) + static_cast<size_t>(h) * Bh * T * D * 2, hb));
+    }
+  }
+  SF_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+  SF_CUDA(cudaStreamWaitEvent(st0, c->ev_join, 0));
+  return 0;
+}
+
 int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int pix_dtype, int B, int T,
                  int Hh, int Ww, void* last_hidden, void* pooler, void* const* hidden_states,
                  void* const* attentions, void* ws, size_t ws_bytes, bool dev_seen = false) {
@@ -512,6 +588,13 @@ int forward_impl(sf_ctx* c, cudaStream_t st, sf_kv* kv, const void* pixels, int 
   const int P = c->cfg.patch_size, D = c->D;
   const int S = (Hh / P) * (Ww / P);
   const long M = static_cast<long>(B) * T * S;
+  if (!kv && !hidden_states && !attentions && B >= 2 && (B % 2) == 0 && dual_stream_enabled() && !prof_enabled() &&
+      !phase_prof_enabled() && M >= 2 * 4096) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone)
+      return forward_dual(c, st, pixels, pix_dtype, B, T, Hh, Ww, last_hidden, pooler, ws, ws_bytes);
+  }
   int time_off = 0, time_total = T;
   if (kv) {
     if (kv->B != B || kv->S != S) {
@@ -821,6 +904,7 @@ uint64_t sf_launch_count(void) { return launch_count(); }
 int sf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_chain") == 0) { set_gemm_chain(value); return 0; }
   if (name && strcmp(name, "stream_graph") == 0) { g_stream_graph_opt = value; return 0; }
+  if (name && strcmp(name, "dual_stream") == 0) { g_dual_stream_opt = value; return 0; }
   set_error("sf_set_option: unknown option '%s'", name ? name : "(null)");
   return SF_ERR_INVALID;
 }
@@ -873,6 +957,9 @@ int sf_destroy(sf_ctx* c) {
   DeviceGuard dg(c->device);
   if (c->arena) cudaFree(c->arena);
   if (c->pos_alt) cudaFree(c->pos_alt);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
   return 0;
 }
@@ -1055,7 +1142,7 @@ int sf_workspace_bytes(const sf_ctx* c, int B, int T, int Hh, int Ww, size_t* ou
   const long M = static_cast<long>(B) * T * S;
   size_t layer = static_cast<size_t>(M) * c->D * 2 + 256 + layer_ws_bytes(c, M);
   size_t head = static_cast<size_t>(M) * c->D * 2 + 256 + head_ws_bytes(c, static_cast<long>(B) * T, S);
-  *out = (layer > head ? layer : head) + 4096;
+  *out = (layer > head ? layer : head) + 4096 + 65536;   // slack for the two-half carve-up of the dual-stream forward
   return 0;
 }
 

@@ -667,3 +667,33 @@ def test_odd_shapes_vs_oracle(B, T, dtype):
     t = TOL[dtype]
     check("last_hidden_state", out.last_hidden_state, ref["last_hidden_state"], t["lhs"], t["cos"])
     check("pooler_output", out.pooler_output, ref["pooler_output"], t["pool"], t["cos"])
+
+
+def test_dual_stream_forward_equals_single_stream():
+    """The one-shot forward of an even batch runs as two half batches on two streams (runtime.cu forward_dual):
+    same kernels per clip, so the outputs must equal the single-stream schedule's (within rounding when the
+    half batch picks other GEMM tile shapes), back-to-back calls must not race on the shared workspace, and
+    work queued on the caller's stream afterwards must see the finished result."""
+    from streamformer_b200 import _native as N
+    cfg = O.OracleConfig(num_hidden_layers=2)
+    w = O.make_weights(cfg, seed=71, style="stress")
+    model = build_model(cfg, w)
+    px = [torch.from_numpy(O.make_pixels(4, 16, cfg, seed=71 + i)).cuda() for i in range(3)]
+    with torch.no_grad():
+        N.set_option("dual_stream", 0)
+        try:
+            single = [model(p) for p in px]
+        finally:
+            N.set_option("dual_stream", -1)
+        n0 = N.launch_count()
+        dual = [model(p) for p in px]                    # back to back: three forwards in flight
+        sums = [d.pooler_output.float().sum() for d in dual]   # consumer work on the caller's stream
+        torch.cuda.synchronize()
+        assert N.launch_count() - n0 > 3 * 2 * 8 * 2 * 0.9, "the dual-stream schedule did not engage"
+    t = TOL[torch.bfloat16]
+    for s, d, sm in zip(single, dual, sums):
+        check("dual vs single last_hidden_state", d.last_hidden_state, s.last_hidden_state.float().cpu().numpy(), t["lhs"] / 4, 0.99995)
+        check("dual vs single pooler_output", d.pooler_output, s.pooler_output.float().cpu().numpy(), t["pool"] / 4, 0.99995)
+        assert abs(float(sm) - float(d.pooler_output.float().sum())) < 1e-3
+    ref = O.forward(w, cfg, px[0][2:3].cpu().numpy())
+    check("dual vs oracle", dual[0].last_hidden_state[2:3], ref["last_hidden_state"], t["lhs"], t["cos"])
