@@ -670,7 +670,7 @@ def test_odd_shapes_vs_oracle(B, T, dtype):
 
 
 def test_dual_stream_forward_equals_single_stream():
-    """The one-shot forward of an even batch runs as two half batches on two streams (runtime.cu forward_dual):
+    """Opt-in schedule: the one-shot forward of an even batch as two half batches on two streams (runtime.cu forward_dual):
     same kernels per clip, so the outputs must equal the single-stream schedule's (within rounding when the
     half batch picks other GEMM tile shapes), back-to-back calls must not race on the shared workspace, and
     work queued on the caller's stream afterwards must see the finished result."""
@@ -686,9 +686,13 @@ def test_dual_stream_forward_equals_single_stream():
         finally:
             N.set_option("dual_stream", -1)
         n0 = N.launch_count()
-        dual = [model(p) for p in px]                    # back to back: three forwards in flight
-        sums = [d.pooler_output.float().sum() for d in dual]   # consumer work on the caller's stream
-        torch.cuda.synchronize()
+        N.set_option("dual_stream", 1)
+        try:
+            dual = [model(p) for p in px]                    # back to back: three forwards in flight
+            sums = [d.pooler_output.float().sum() for d in dual]   # consumer work on the caller's stream
+            torch.cuda.synchronize()
+        finally:
+            N.set_option("dual_stream", -1)
         assert N.launch_count() - n0 > 3 * 2 * 8 * 2 * 0.9, "the dual-stream schedule did not engage"
     t = TOL[torch.bfloat16]
     for s, d, sm in zip(single, dual, sums):
