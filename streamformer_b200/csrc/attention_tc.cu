@@ -20,8 +20,13 @@
 // SK/2 columns) during the second softmax pass, and the O accumulator (64 columns at +128) reuses the
 // then-dead upper half of S.  The two regions let the S/PV MMAs of one M tile run under the softmax
 // of the other.  exp2 runs on MUFU in the log2 domain with the 1/8 scale folded in.
+//
+// This is the GENERAL kernel (any S <= 208).  224x224 frames (S = 196) take spatial_attn_row_kernel further
+// down: whole score rows in registers, 43 us instead of 60 us at cfg2 shapes.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
+#include <stdio.h>
 
 #include <type_traits>
 
@@ -63,7 +68,26 @@ template <> struct Fmt<__nv_bfloat16> { static constexpr int value = 1; };
 #ifndef SF_EXP2_POLY_PER4
 #define SF_EXP2_POLY_PER4 0
 #endif
-constexpr int kExp2PolyPer4 = SF_EXP2_POLY_PER4;     // of every 4 consecutive elements, how many use exp2_fma
+constexpr int kExp2PolyPer4 = SF_EXP2_POLY_PER4;
+// Packing two non-negative fp32 probabilities into a bf16 pair.  F2FP (cvt.rn.bf16x2.f32) shares the quarter-rate XU
+// pipe with MUFU.EX2; for bf16 the upper halves of the two words taken by one PRMT (ALU pipe) are the truncated values.
+// With the exponent argument shifted by log2(1 + 2^-9) truncation errs by (-2^-9, +2^-9) relative, centred like
+// round-to-nearest, and the row sum is taken from the same shifted fp32 values, so the normalisation is consistent.
+#ifndef SF_PACK_PRMT
+#define SF_PACK_PRMT 1
+#endif
+template <typename T> struct PPack {
+  static constexpr float kShift = 0.f;
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { return Pack2<T>::pack(lo, hi); }
+};
+#if SF_PACK_PRMT
+template <> struct PPack<__nv_bfloat16> {
+  static constexpr float kShift = 0.0028150156f;       // log2(1 + 2^-9)
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+  }
+};
+#endif     // of every 4 consecutive elements, how many use exp2_fma
 __device__ __forceinline__ float exp2_fma(float x) {
   x = fmaxf(x, -120.0f);
   const float magic = 12582912.0f;                    // 1.5 * 2^23
@@ -313,10 +337,303 @@ spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Round-2 kernel for 224x224 frames (193 <= S <= 200): every softmax thread holds its WHOLE score row in registers.
+//
+// What the round-1 kernel above is bound by (clock64 timelines, profiles/r2_spatial_attention_timeline.md): not the
+// MUFU pipe, not tensor-memory bandwidth (a microbenchmark reads 400+ B/clk per SM), but the per-warp chain of
+// 16-column tcgen05.ld -> compute -> tcgen05.st round trips, twice over the row, with two warps per scheduler.
+// Spreading a row over 2-3 warps (tried: 58.8 / 66.7 us) only adds barriers.  Here, as in FlashAttention-4, a
+// softmax warpgroup takes registers from the control warpgroup (setmaxnreg: 232 against 40), loads the 200 score
+// columns of its row with four tcgen05.ld, and computes the maximum, the exponentials, the row sum and the packed P
+// branch-free out of registers: one read of S, no cross-warp exchange, one dependent TMEM round trip per row.
+//
+//   warp 0      TMA producer
+//   warp 1 / 2  MMA issuer of M tile 0 / 1: S -> (softmax) -> PV per item, each on its own barriers
+//   warps 4-7   softmax + read-out of M tile 0 (TMEM region 0: S/P at columns [0, 208), O apart at [416, 480) so that
+//               S of the next item only waits for PV, not for the read-out)
+//   warps 8-11  the same for M tile 1 (region 1: S/P at [208, 416), O in the dead score columns [336, 400))
+// The two tiles free-run; `skew` delays tile 1's first S so that its exponential phase falls into tile 0's
+// load / maximum / read-out phases (the MUFU pipe is the one resource both need at full rate).
+constexpr int kDefaultSkew = 3500;                              // cycles; sweep on B200: 0 -> 46.1 us, 2500 -> 44.2, 3500 -> 43.3
+constexpr int kRowOcts = 25;                                    // 8-column groups held per thread (200 columns)
+constexpr int kReg1Col = kMaxKeys;                              // region 1 starts right behind region 0's scores
+constexpr int kO0Col = 2 * kMaxKeys;                            // O of region 0
+constexpr int kSoftmaxRegs = 232, kControlRegs = 40;
+constexpr int kHalfKSteps = 7;                                  // PV k-steps (16 keys each) issued after the first half of P
+constexpr int kSmemBytesRow = 2 * kStageBytes + 1024 + 8 * 4096 + 1024;   // + one 32 x 128 B output tile per softmax warp
+
+#ifdef SF_ATTN_TIMELINE
+#define SF_TL(...) __VA_ARGS__
+#else
+#define SF_TL(...)
+#endif
+
+struct SpatialRowArgs {
+  SpatialTcArgs a;
+  int skew;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(384, 1)
+spatial_attn_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        const __grid_constant__ CUtensorMap tmO, const SpatialRowArgs ra) {
+  const SpatialTcArgs& a = ra.a;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes);
+  uint64_t* kv_empty = kv_full + 2;
+  uint64_t* s_full = kv_empty + 2;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 2;
+  uint64_t* region_free = o_full + 2;
+  uint64_t* p_half = region_free + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);      // one commit per tile's issuer
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);        // the four softmax warps of the tile
+      mbar_init(&p_half[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&region_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch_dependents();
+
+  const int D = a.heads * kHd;
+  const int nitems = (a.items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1;
+  if (warp < 4) {
+    setmaxnreg_dec<kControlRegs>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      if (elect_one_sync()) {
+        for (int i = 0; i < nitems; ++i) {
+          const int item = blockIdx.x + i * gridDim.x;
+          const int st = i & 1;
+          const uint32_t ph = (i >> 1) & 1;
+          const int frame = item / a.heads, h = item % a.heads;
+          const int b = a.T_inner > 1 ? frame / a.T_inner : frame;
+          const int t = a.T_inner > 1 ? frame % a.T_inner : 0;
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          uint8_t* base = smem + st * kStageBytes;
+          mbar_arrive_expect_tx(&kv_full[st], static_cast<uint32_t>(2 * kQTileBytes + 2 * a.SK * 128));
+          tma_load_4d(base, &tmQ, &kv_full[st], h * kHd, t, 0, b);
+          tma_load_4d(base + 2 * kQTileBytes, &tmKV, &kv_full[st], D + h * kHd, t, 0, b);
+          tma_load_4d(base + kQTileBytes, &tmQ, &kv_full[st], h * kHd, t, 128, b);
+          tma_load_4d(base + 2 * kQTileBytes + kKVTileBytes, &tmKV, &kv_full[st], 2 * D + h * kHd, t, 0, b);
+        }
+      }
+    } else if (warp <= 2) {
+      // ---------------------------------------------------------------- MMA issuer of tile r
+      const int r = warp - 1;
+      if (elect_one_sync()) {
+        const uint32_t idesc_s = umma_idesc_f16(128, a.SK, Fmt<T>::value, 0);
+        const uint32_t idesc_pv = umma_idesc_f16(128, kHd, Fmt<T>::value, 1);
+        const int ksteps_pv = a.SK / 16;
+        const uint32_t d_s = tmem_base + (r ? kReg1Col : 0);
+        const uint32_t d_o = tmem_base + (r ? kReg1Col + kOCol : kO0Col);
+        for (int i = 0; i < nitems; ++i) {
+          const int st = i & 1;
+          const uint32_t par = i & 1;
+          const uint32_t sbase = smem_u32(smem + st * kStageBytes);
+          mbar_wait(&kv_full[st], (i >> 1) & 1);
+          if (r == 1 && i == 0 && ra.skew > 0) {      // de-phase the two tiles once the first operands have landed
+            const long long t0 = clock64();
+            while (clock64() - t0 < ra.skew) {}
+          }
+          // tile 0: P of the previous item is dead once its PV has retired; tile 1: its O sits inside the score
+          // columns, so the read-out has to be over as well
+          if (r == 0) mbar_wait(&o_full[0], par ^ 1);
+          else mbar_wait(&region_free[1], par ^ 1);
+          tc_fence_after();
+          const uint64_t dq = umma_desc_sw128_kmajor(sbase + r * kQTileBytes);
+          const uint64_t dk = umma_desc_sw128_kmajor(sbase + 2 * kQTileBytes);
+#pragma unroll
+          for (int k = 0; k < kHd / 16; ++k) umma_f16(d_s, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[r]);
+          const uint64_t dv = umma_desc_sw128_mnmajor(sbase + 2 * kQTileBytes + kKVTileBytes);
+          mbar_wait(&p_half[r], par);                 // P of keys 0 .. 111 is in tensor memory
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kHalfKSteps; ++k)
+            umma_f16_ts(d_o, d_s + k * 8, dv + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, k > 0 ? 1u : 0u);
+          mbar_wait(&p_full[r], par);
+          tc_fence_after();
+          for (int k = kHalfKSteps; k < ksteps_pv; ++k)
+            umma_f16_ts(d_o, d_s + k * 8, dv + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, 1u);
+          umma_commit(&o_full[r]);
+          umma_commit(&kv_empty[st]);   // this tile's MMAs that read the stage's smem have retired
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax + read-out of tile r, thread = row
+    setmaxnreg_inc<kSoftmaxRegs>();
+    const int r = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int n = r * 128 + quarter * 32 + lane;          // token (query row) of this thread
+    const bool warp_valid = (r * 128 + quarter * 32) < a.S;
+    const uint32_t t_s = tmem_base + (r ? kReg1Col : 0) + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_o = tmem_base + (r ? kReg1Col + kOCol : kO0Col) + (static_cast<uint32_t>(quarter * 32) << 16);
+    SF_TL(__shared__ int tlog[2 * 12 * 7]; long long tbase = 0;)
+    uint8_t* otile = smem + 2 * kStageBytes + 1024 + (warp - 4) * 4096;   // 1024-byte aligned: TMA's 128B swizzle
+    for (int i = 0; i < nitems; ++i) {
+      const int item = blockIdx.x + i * gridDim.x;
+      const uint32_t par = i & 1;
+      float l = 0.f;
+      SF_TL(long long tl0 = clock64(); long long tl1 = 0, tl2 = 0, tl3 = 0, tl4 = 0, tl5 = 0; if (i == 0) tbase = tl0;)
+      mbar_wait(&s_full[r], par);
+      SF_TL(tl1 = clock64();)
+      tc_fence_after();
+      if (warp_valid) {
+        uint32_t v[kRowOcts * 8];
+        tmem_ld_32x32b_x64(t_s, v);
+        tmem_ld_32x32b_x64(t_s + 64, v + 64);
+        tmem_ld_32x32b_x64(t_s + 128, v + 128);
+        tmem_ld_32x32b_x8(t_s + 192, *reinterpret_cast<uint32_t (*)[8]>(v + 192));
+        tmem_ld_wait();
+        // keys S .. 199 (zero-filled K rows) out of the maximum and the sum
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (192 + j >= a.S) v[192 + j] = 0xff800000u;     // -inf
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kRowOcts * 8; j += 8) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+        }
+        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        SF_TL(tl2 = clock64();)
+        const float nm = fmaf(-mx, a.scale_log2, PPack<T>::kShift);
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+        for (int o = 0; o < kRowOcts; ++o) {
+          float pj[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = fmaf(__uint_as_float(v[o * 8 + j]), a.scale_log2, nm);
+            if ((j % 4) < kExp2PolyPer4) {
+              pj[j] = exp2_fma(x);
+            } else {
+              float e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+              pj[j] = e;
+            }
+          }
+          l0 += pj[0] + pj[1];
+          l1 += pj[2] + pj[3];
+          l2 += pj[4] + pj[5];
+          l3 += pj[6] + pj[7];
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pk[j] = PPack<T>::pack(pj[2 * j], pj[2 * j + 1]);
+          tmem_st_32x32b_x4(t_s + o * 4, pk);
+          if (o == 2 * kHalfKSteps - 1) {       // first half of P complete: the tensor pipe starts on PV under the rest
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_half[r]);
+          }
+        }
+        if (a.SK > kRowOcts * 8) {         // keys 200 .. 207: V rows are zero, P must be finite
+          const uint32_t z[4] = {0u, 0u, 0u, 0u};
+          tmem_st_32x32b_x4(t_s + kRowOcts * 4, z);
+        }
+        l = (l0 + l1) + (l2 + l3);
+        tmem_st_wait();
+      }
+      SF_TL(tl3 = clock64();)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (!warp_valid) mbar_arrive(&p_half[r]);
+        mbar_arrive(&p_full[r]);
+      }
+
+      // read-out: O / l, the 64 contiguous elements of this thread's token
+      mbar_wait(&o_full[r], par);
+      SF_TL(tl4 = clock64();)
+      tc_fence_after();
+      if (warp_valid) {
+        uint32_t o[64];
+        tmem_ld_32x32b_x64(t_o, o);
+        const float inv = 1.0f / l;
+        tmem_ld_wait();
+        // O is in registers: hand the region back BEFORE the global stores (an mbarrier arrive is a release; behind the
+        // stores it waited ~1.5 k cycles for them to drain)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&region_free[r]);
+        SF_TL(tl5 = clock64();)
+        // 32 rows x 128 B into this warp's shared-memory tile in TMA's 128-byte swizzle (16-byte chunk c of row lane at
+        // chunk c ^ (lane & 7): conflict-free), then ONE bulk tensor store per warp: the 4-D map addresses token n of
+        // frame (b,t) at row (b*S + n)*T + t and clips rows >= S.  (Per-thread stores cost ~2 k cycles of LSU time per
+        // item, coalesced st.global through shared memory still ~1.5 k of store back-pressure in the softmax chain.)
+        if (lane == 0) tma_store_wait_read<0>();       // the previous item's store has read the tile
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 w;
+          w.x = Pack2<T>::pack(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+          w.y = Pack2<T>::pack(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+          w.z = Pack2<T>::pack(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+          w.w = Pack2<T>::pack(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+          *reinterpret_cast<uint4*>(otile + lane * 128 + ((q ^ (lane & 7)) << 4)) = w;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int frame = item / a.heads, h = item % a.heads;
+          const int b = a.T_inner > 1 ? frame / a.T_inner : frame;
+          const int t = a.T_inner > 1 ? frame % a.T_inner : 0;
+          tma_store_4d(&tmO, otile, h * kHd, t, n, b);   // n of lane 0 = first token of this warp's 32 rows
+          tma_store_commit();
+        }
+      }
+      if (!warp_valid) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&region_free[r]);
+      }
+      SF_TL(if (blockIdx.x == 0 && lane == 0 && quarter == 0 && i < 12) { int* q = tlog + (r * 12 + i) * 7; q[0] = (int)(tl0 - tbase); q[1] = (int)(tl1 - tl0); q[2] = (int)(tl2 - tl0); q[3] = (int)(tl3 - tl0); q[4] = (int)(tl4 - tl0); q[5] = (int)(clock64() - tl0); q[6] = (int)(tl5 - tl0); })
+    }
+    if (lane == 0) tma_store_wait<0>();                // bulk stores out of this CTA's shared memory have completed
+    SF_TL(if (blockIdx.x == 0 && lane == 0 && quarter == 0) for (int i = 0; i < nitems && i < 12; ++i) { int* q = tlog + (r * 12 + i) * 7; printf("tile %d item %2d: start %6d | s_full +%d max +%d exp+st +%d o_full +%d O loaded +%d out +%d\n", r, i, q[0], q[1], q[2], q[3], q[4], q[6], q[5]); })
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // 4-D view of the fused QKV activation: (column, t, n, b) with token n of frame (b,t) at row
 // (b*S + n)*T + t; T = 1 describes contiguous frames.  Box = 64 columns x 1 x box_rows tokens x 1.
 int make_frame_map(CUtensorMap* map, int dtype, const void* base, int ld, int ncols, int T, int S, int Bf,
-                   int box_rows) {
+                   int box_rows, bool store = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -3;
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(ncols), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(S),
@@ -327,7 +644,8 @@ int make_frame_map(CUtensorMap* map, int dtype, const void* base, int ld, int nc
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMapDataType dt = dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = fn(map, dt, 4, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_128B, store ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(frame map) failed (%d): ld=%d T=%d S=%d B=%d box=%d", (int)r, ld, T, S, Bf, box_rows);
     return -3;
@@ -357,24 +675,43 @@ int spatial_attention_tc(cudaStream_t stream, int dtype, const void* qkv, int ld
   a.items = frames * heads;
   a.scale_log2 = scale * kLog2e;
   const int grid = a.items < num_sms() ? a.items : num_sms();
+  // 224x224 frames take the row-in-registers kernel (SF_SPATIAL_ROW=0 forces the general one); SF_SPATIAL_SKEW = start
+  // offset of tile 1 in cycles.
+  static const bool row_on = [] { const char* e = getenv("SF_SPATIAL_ROW"); return !(e && e[0] == '0'); }();
+  static const int skew = [] { const char* e = getenv("SF_SPATIAL_SKEW"); return e ? atoi(e) : kDefaultSkew; }();
+  const bool row = row_on && S > (kRowOcts - 1) * 8 && S <= kRowOcts * 8 && ld_out % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   cudaError_t e;
   {
     ProfScope ps(stream, kProfSpatialAttn, 4.0 * frames * heads * static_cast<double>(S) * S * kHd,
                  2.0 * frames * heads * kHd * 4.0 * S);
-    LaunchCfg lc(dim3(static_cast<unsigned>(grid)), dim3(384), kSmemBytes, stream);
-    if (dtype == kBF16) {
-      static bool attr = false;
-      if (!attr) {
-        cudaFuncSetAttribute(spatial_attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        attr = true;
+    LaunchCfg lc(dim3(static_cast<unsigned>(grid)), dim3(384), row ? kSmemBytesRow : kSmemBytes, stream);
+    static bool attr_set[4] = {false, false, false, false};
+    auto set_attr = [&](auto kern, bool* attr) {
+      if (!*attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, row ? kSmemBytesRow : kSmemBytes);
+        *attr = true;
       }
+    };
+    if (row) {
+      CUtensorMap tmO;
+      rc = make_frame_map(&tmO, dtype, out, ld_out, heads * kHd, T, S, Bf, 32, true);
+      if (rc) return rc;
+      SpatialRowArgs ra;
+      ra.a = a;
+      ra.skew = skew;
+      if (dtype == kBF16) {
+        set_attr(spatial_attn_row_kernel<__nv_bfloat16>, &attr_set[0]);
+        e = cudaLaunchKernelEx(&lc.cfg, spatial_attn_row_kernel<__nv_bfloat16>, tmQ, tmKV, tmO, ra);
+      } else {
+        set_attr(spatial_attn_row_kernel<__half>, &attr_set[1]);
+        e = cudaLaunchKernelEx(&lc.cfg, spatial_attn_row_kernel<__half>, tmQ, tmKV, tmO, ra);
+      }
+    } else if (dtype == kBF16) {
+      set_attr(spatial_attn_tc_kernel<__nv_bfloat16>, &attr_set[2]);
       e = cudaLaunchKernelEx(&lc.cfg, spatial_attn_tc_kernel<__nv_bfloat16>, tmQ, tmKV, a);
     } else {
-      static bool attr = false;
-      if (!attr) {
-        cudaFuncSetAttribute(spatial_attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        attr = true;
-      }
+      set_attr(spatial_attn_tc_kernel<__half>, &attr_set[3]);
       e = cudaLaunchKernelEx(&lc.cfg, spatial_attn_tc_kernel<__half>, tmQ, tmKV, a);
     }
   }
