@@ -296,6 +296,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Weight operand of this CTA's first tile, started ahead of the dependency wait (GemmEpilogue::w_static): the first
+  // pre_b K blocks of W go into the stages / ring slots the main loop would put them in anyway.  Slot path: only K
+  // blocks whose A part is resident (kb < res_kb) — for those the ring sees B blocks only, in this order.
+  int pre_b = 0;
+  if (p.epi.w_static) {
+    TileWalk w0(p.M, p.N, kTileM, BN, group, worker, num_workers);
+    if (w0.valid()) {
+      if constexpr (kSlotPath) pre_b = res_kb < ring ? res_kb : ring;
+      else pre_b = kStages < k_blocks ? kStages : k_blocks;
+      if (warp == 0 && elect_one_sync()) {
+        const int n0 = w0.n_tile() * BN + static_cast<int>(cta_rank) * (BN / CG);
+        for (int kb = 0; kb < pre_b; ++kb) {
+          if constexpr (kSlotPath) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * L::kSlotBytes);
+            tma_load_2d_cg2(smem + (res_kb + kb) * L::kSlotBytes, &tmB, &full_bar[kb], kb * kBK, n0);
+          } else if constexpr (CG == 2) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * L::kStageBytes);
+            tma_load_2d_cg2(smem + kb * L::kStageBytes + L::kABytes, &tmB, &full_bar[kb], kb * kBK, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[kb], L::kStageBytes);
+            tma_load_2d(smem + kb * L::kStageBytes + L::kABytes, &tmB, &full_bar[kb], kb * kBK, n0);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
   // PDL: everything above overlapped the tail of the previous kernel; from here on we read its output
   griddep_wait();
   griddep_launch_dependents();
@@ -317,6 +344,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_load_2d_cg2(ring_base + slot * L::kSlotBytes, tm, &full_bar[slot], c0, c1);
           if (++slot == ring) { slot = 0; phase ^= 1; }
         };
+        bool first_tile = true;
         for (TileWalk w(p.M, p.N, kTileM, BN, group, worker, num_workers); w.valid(); w.next()) {
           const int m0 = w.m_tile() * kTileM + static_cast<int>(cta_rank) * kBM;
           const int n0 = w.n_tile() * BN + static_cast<int>(cta_rank) * (BN / CG);
@@ -331,30 +359,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             } else {
               ring_load(&tmA, kb * kBK, m0);
             }
-            ring_load(&tmB, kb * kBK, n0);
+            if (first_tile && kb < pre_b) {          // this W block went out ahead of griddepcontrol.wait
+              if (++slot == ring) { slot = 0; phase ^= 1; }
+            } else {
+              ring_load(&tmB, kb * kBK, n0);
+            }
           }
+          first_tile = false;
           if (w.last_in_item()) ++items_done;
         }
       }
     } else if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (TileWalk w(p.M, p.N, kTileM, BN, 1, worker, num_workers); w.valid(); w.next()) {
+      bool first_tile = true;
+      for (TileWalk w(p.M, p.N, kTileM, BN, 1, worker, num_workers); w.valid(); w.next(), first_tile = false) {
         const int m0 = w.m_tile() * kTileM + static_cast<int>(cta_rank) * kBM;
         const int n0 = w.n_tile() * BN + static_cast<int>(cta_rank) * (BN / CG);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
+          const bool w_sent = first_tile && kb < pre_b;    // expect_tx armed and W loaded ahead of the dependency wait
           if constexpr (CG == 2) {
             // the leader's barrier counts the bytes of both CTAs' loads for this stage
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            if (leader && !w_sent) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
             tma_load_2d_cg2(sa, &tmA, &full_bar[stage], kb * kBK, m0);
-            tma_load_2d_cg2(sb, &tmB, &full_bar[stage], kb * kBK, n0);
+            if (!w_sent) tma_load_2d_cg2(sb, &tmB, &full_bar[stage], kb * kBK, n0);
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            if (!w_sent) mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n0);
+            if (!w_sent) tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n0);
           }
           if (++stage == kStages) {
             stage = 0;

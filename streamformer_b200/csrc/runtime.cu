@@ -262,9 +262,12 @@ int carve_layer_ws(const sf_ctx* c, long M, Bump& b, WsPlan& p) {
   return 0;
 }
 
+// Both helpers describe GEMMs against packed weights of this context (sf_bind_weights synchronises the stream before it
+// returns, so no kernel in flight writes them): the W operand may be fetched ahead of the PDL dependency wait.
 GemmEpilogue epi_bias(const float* bias) {
   GemmEpilogue e;
   e.bias = bias;
+  e.w_static = true;
   return e;
 }
 
@@ -272,6 +275,7 @@ GemmEpilogue epi_ln(const float* bias, const float* colsum, const float2* stats,
   GemmEpilogue e;
   e.bias = bias;
   e.ln_colsum = colsum; e.ln_stats = stats; e.ln_parts = parts; e.ln_eps = eps;
+  e.w_static = true;
   return e;
 }
 
@@ -297,7 +301,8 @@ int run_gemms(sf_ctx* c, cudaStream_t st, GemmCall* calls, int n, const WsPlan& 
     return gemm_chain(st, dt, calls, n, w.chain_ctr);
   }
   for (int i = 0; i < n; ++i) {
-    const GemmCall& g = calls[i];
+    GemmCall& g = calls[i];
+    g.epi.w_static = true;     // W is a packed weight; sf_bind_weights synchronises the stream before it returns
     SF_CHECK(gemm(st, dt, g.A, g.lda, g.W, g.ldw, g.out, g.ldo, g.M, g.N, g.K, g.epi));
   }
   return 0;

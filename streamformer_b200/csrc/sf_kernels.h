@@ -50,6 +50,10 @@ struct GemmEpilogue {
   // Partial row statistics of the OUTPUT rows (values as rounded to the activation dtype), one
   // (sum, sumsq) per row and column group, for the next folded LayerNorm: [gemm_stats_parts(M,N)][M]
   float2* stats_out = nullptr;
+  // W is a bound (packed) weight that no kernel launched right before this GEMM writes: the producer warp may start
+  // the weight half of its first operand stages BEFORE griddepcontrol.wait, under the previous kernel's tail.  The
+  // launcher drops the flag when the previous launch of the process was a weight-writing (bind / fold) kernel.
+  bool w_static = false;
 };
 
 // C[M,N] = A[M,K] . W[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
