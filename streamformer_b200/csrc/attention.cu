@@ -481,6 +481,131 @@ temporal_decode_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
   }
 }
 
+// Streaming decode, register-direct form (round 2, the default): the same contract as temporal_decode_kernel
+// above, but the history goes global -> registers with 16-byte loads and the arithmetic runs on the FMA pipe.
+//
+// Why: at 32+ cached frames a (site, head) task is 8.7 KB of K/V; the TMA-ring kernel above has room for ONE
+// stage per warp there (16 KB of staging x 12 warps), so every warp alternates between waiting for its history
+// and a latency-bound ldmatrix -> mma.sync -> softmax -> mma.sync chain: 30 us per layer at 34 frames = 2.7 TB/s
+// of an 82 MB read (ncu launch list, profiles/r2_stream_step.md).  The arithmetic is 2 x 64 x T MACs per task —
+// nothing a tensor core is needed for — so this kernel drops shared memory, barriers and mma altogether:
+//   lane = (r = lane / 8, c = lane % 8): rows j = j0 + 4 i + r of a 32-row batch, 16-byte chunk c of the row;
+//   one load instruction fetches 4 consecutive 128-byte rows, the 16 independent loads (K and V) of a batch are
+//   in flight together, 16 warps per SM (a 16-row double-buffered variant measured slower: 26.3 vs 25.0 us);
+//   scores: 8-lane dot products (3 shuffles per 4 rows), online softmax over batches, P stays fp32;
+//   O: every lane accumulates its rows' p x v for its 8 dims, two shuffle steps fold the four row groups.
+// The cache rows of a warp's first task are requested BEFORE griddepcontrol.wait (they do not depend on the QKV
+// GEMM); the new frame's key / value come from the QKV buffer and are appended to the cache by the lanes that
+// own row `seen`.
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+temporal_decode_direct_kernel(const TemporalArgs a, T* __restrict__ kc, T* __restrict__ vc, int Tcap) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane >> 3, c = lane & 7;
+  const int seen = a.seen_dev ? *a.seen_dev : a.q_off;     // frames cached before this step
+  const long nwarps = static_cast<long>(gridDim.x) * (blockDim.x >> 5);
+  const long task0 = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  const long task_stride = static_cast<long>(Tcap) * kHd;
+  const int D = a.heads * kHd;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+  uint4 kk[8], vv[8];
+  // cache rows j0 + 4 i + r (< seen) of `task`
+  auto load_batch = [&](long task, int j0) {
+    const T* kb = kc + task * task_stride + c * 8;
+    const T* vb = vc + task * task_stride + c * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = j0 + 4 * i + r;
+      kk[i] = zero4;
+      vv[i] = zero4;
+      if (j < seen) {
+        kk[i] = __ldcs(reinterpret_cast<const uint4*>(kb + static_cast<long>(j) * kHd));
+        vv[i] = __ldcs(reinterpret_cast<const uint4*>(vb + static_cast<long>(j) * kHd));
+      }
+    }
+  };
+  if (task0 < a.tasks) load_batch(task0, 0);   // the history does not depend on the QKV GEMM
+  griddep_wait();               // from here on: q / k_new / v_new written by the QKV GEMM
+  griddep_launch_dependents();
+
+  for (long task = task0; task < a.tasks; task += nwarps) {
+    const long site = task / a.heads;
+    const int h = static_cast<int>(task - site * a.heads);
+    const T* row = reinterpret_cast<const T*>(a.q) + site * a.q_ld + h * kHd + c * 8;
+    const uint4 q4 = *reinterpret_cast<const uint4*>(row);
+    const uint4 knew = *reinterpret_cast<const uint4*>(row + D);
+    const uint4 vnew = *reinterpret_cast<const uint4*>(row + 2 * D);
+    float qf[8];
+    {
+      const float2 q0 = Pack2<T>::unpack(q4.x), q1 = Pack2<T>::unpack(q4.y), q2 = Pack2<T>::unpack(q4.z), q3 = Pack2<T>::unpack(q4.w);
+      qf[0] = q0.x * a.scale_log2; qf[1] = q0.y * a.scale_log2; qf[2] = q1.x * a.scale_log2; qf[3] = q1.y * a.scale_log2;
+      qf[4] = q2.x * a.scale_log2; qf[5] = q2.y * a.scale_log2; qf[6] = q3.x * a.scale_log2; qf[7] = q3.y * a.scale_log2;
+    }
+    if (r == (seen & 3)) {        // fused kv_append: cache[site][head][seen][:] = new row
+      *reinterpret_cast<uint4*>(kc + task * task_stride + static_cast<long>(seen) * kHd + c * 8) = knew;
+      *reinterpret_cast<uint4*>(vc + task * task_stride + static_cast<long>(seen) * kHd + c * 8) = vnew;
+    }
+    float m_run = -INFINITY, l_part = 0.f;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j0 = 0; j0 <= seen; j0 += 32) {
+      if (j0 > 0 || task != task0) load_batch(task, j0);
+      float sc[8];
+      float bm = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sc[i] = -INFINITY;
+        if (j0 + 4 * i <= seen) {     // warp-uniform: the row group holds at least one valid key
+          const int j = j0 + 4 * i + r;
+          if (j == seen) { kk[i] = knew; vv[i] = vnew; }
+          const float2 k0 = Pack2<T>::unpack(kk[i].x), k1 = Pack2<T>::unpack(kk[i].y), k2 = Pack2<T>::unpack(kk[i].z), k3 = Pack2<T>::unpack(kk[i].w);
+          float d = qf[0] * k0.x;
+          d = fmaf(qf[1], k0.y, d); d = fmaf(qf[2], k1.x, d); d = fmaf(qf[3], k1.y, d);
+          d = fmaf(qf[4], k2.x, d); d = fmaf(qf[5], k2.y, d); d = fmaf(qf[6], k3.x, d); d = fmaf(qf[7], k3.y, d);
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if (j <= seen) sc[i] = d;
+          bm = fmaxf(bm, sc[i]);
+        }
+      }
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+      const float m_new = fmaxf(m_run, bm);       // finite: every batch holds at least one valid key
+      const float resc = exp2f(m_run - m_new);    // 0 on the first batch
+      l_part *= resc;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) o[d] *= resc;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (j0 + 4 * i <= seen) {
+          const float pj = exp2f(sc[i] - m_new);  // masked keys: exp2(-inf) = 0
+          l_part += pj;
+          const float2 v0 = Pack2<T>::unpack(vv[i].x), v1 = Pack2<T>::unpack(vv[i].y), v2 = Pack2<T>::unpack(vv[i].z), v3 = Pack2<T>::unpack(vv[i].w);
+          o[0] = fmaf(pj, v0.x, o[0]); o[1] = fmaf(pj, v0.y, o[1]); o[2] = fmaf(pj, v1.x, o[2]); o[3] = fmaf(pj, v1.y, o[3]);
+          o[4] = fmaf(pj, v2.x, o[4]); o[5] = fmaf(pj, v2.y, o[5]); o[6] = fmaf(pj, v3.x, o[6]); o[7] = fmaf(pj, v3.y, o[7]);
+        }
+      }
+      m_run = m_new;
+    }
+    // fold the four row groups
+    l_part += __shfl_xor_sync(0xffffffffu, l_part, 8);
+    l_part += __shfl_xor_sync(0xffffffffu, l_part, 16);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      o[d] += __shfl_xor_sync(0xffffffffu, o[d], 8);
+      o[d] += __shfl_xor_sync(0xffffffffu, o[d], 16);
+    }
+    if (r == 0) {
+      const float inv = 1.0f / l_part;
+      uint4 w;
+      w.x = Pack2<T>::pack(o[0] * inv, o[1] * inv); w.y = Pack2<T>::pack(o[2] * inv, o[3] * inv);
+      w.z = Pack2<T>::pack(o[4] * inv, o[5] * inv); w.w = Pack2<T>::pack(o[6] * inv, o[7] * inv);
+      *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + site * a.out_ld + h * kHd + c * 8) = w;
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 kv_append_kernel(const T* __restrict__ qkv, long ld, T* __restrict__ kc, T* __restrict__ vc, int Tcap,
@@ -1433,6 +1558,21 @@ int temporal_decode(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv,
   a.tasks = static_cast<long>(sites) * heads;
   a.scale_log2 = scale * kLog2e;
   a.seen_dev = seen_dev;
+  ProfScope ps(stream, kProfTemporalAttn, 4.0 * sites * heads * static_cast<double>(seen + 1) * kHd,
+               2.0 * sites * heads * kHd * (5.0 + 2.0 * seen));
+  // SF_DECODE_TMA=1 selects the TMA-ring / mma.sync kernel; the default is the register-direct kernel
+  static const bool use_tma = [] { const char* e = getenv("SF_DECODE_TMA"); return e && e[0] == '1'; }();
+  if (!use_tma && (ld_qkv % 8 == 0) && (ld_out % 8 == 0) && (reinterpret_cast<uintptr_t>(qkv) % 16 == 0) &&
+      (reinterpret_cast<uintptr_t>(out) % 16 == 0)) {
+    long blocks = (a.tasks + 7) / 8;
+    if (blocks > 2L * num_sms()) blocks = 2L * num_sms();
+    LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream);
+    if (dtype == kBF16) cudaLaunchKernelEx(&lc.cfg, temporal_decode_direct_kernel<__nv_bfloat16>, a, reinterpret_cast<__nv_bfloat16*>(kcache),
+                                           reinterpret_cast<__nv_bfloat16*>(vcache), Tcap);
+    else cudaLaunchKernelEx(&lc.cfg, temporal_decode_direct_kernel<__half>, a, reinterpret_cast<__half*>(kcache),
+                            reinterpret_cast<__half*>(vcache), Tcap);
+    return check_launch("temporal_decode");
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(temporal_decode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmem);
@@ -1442,8 +1582,6 @@ int temporal_decode(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv,
   const int kDecWarps = dec_warps(Tcap);
   long blocks = (a.tasks + kDecWarps - 1) / kDecWarps;
   if (blocks > num_sms()) blocks = num_sms();
-  ProfScope ps(stream, kProfTemporalAttn, 4.0 * sites * heads * static_cast<double>(seen + 1) * kHd,
-               2.0 * sites * heads * kHd * (5.0 + 2.0 * seen));
   CUtensorMap tmK, tmV;
   int rc = make_cache_map(&tmK, dtype, kcache, static_cast<long>(sites) * heads * Tcap);
   if (rc) return rc;

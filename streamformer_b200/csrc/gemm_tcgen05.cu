@@ -147,6 +147,119 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return fmaf(h, th, h);
 }
 
+// ----------------------------------------------------------------------------- packed fp32 pairs (FFMA2 / FMUL2 / FADD2)
+// sm_100 issues one instruction for two fp32 lanes held in an aligned register pair.  The epilogue warps are
+// ISSUE-bound in the GELU epilogue (fc1: ~23 instructions per output element against a K = 768 main loop), so the
+// bias / LayerNorm-fold / GELU-polynomial / residual arithmetic runs on pairs: the same IEEE operations in the same
+// order per element (results are bit-identical to the scalar form), about 0.7 of the instructions.
+#ifdef SF_GEMM_TIMELINE
+#define SF_GTL(...) __VA_ARGS__
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#else
+#define SF_GTL(...)
+#endif
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_erf() above on a pair
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+  float t0, t1;
+  upk2(mul2(x, x), t0, t1);
+  const f32x2 t = pk2(fminf(t0, 20.25f), fminf(t1, 20.25f));
+  f32x2 p = fma2(pk2(5.838623416e-08f, 5.838623416e-08f), t, pk2(-3.653467351e-06f, -3.653467351e-06f));
+  p = fma2(p, t, pk2(7.064459774e-05f, 7.064459774e-05f));
+  p = fma2(p, t, pk2(5.841390203e-04f, 5.841390203e-04f));
+  p = fma2(p, t, pk2(-1.059873517e-01f, -1.059873517e-01f));
+  p = fma2(p, t, pk2(-2.301437105e+00f, -2.301437105e+00f));
+  float a0, a1, e0, e1, r0, r1;
+  upk2(mul2(x, p), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  upk2(add2(pk2(e0, e1), pk2(1.0f, 1.0f)), a0, a1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(a0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(a1));
+  return mul2(x, pk2(r0, r1));
+}
+// Eight consecutive accumulator columns of one row as four pairs, and the epilogue stages on them.
+struct Epi8 {
+  f32x2 v[4];
+  __device__ __forceinline__ void load(const uint32_t* raw) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = pk2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+  }
+  // v = rstd * (v + nmean * colsum) + bias      (folded LayerNorm)
+  __device__ __forceinline__ void ln_fold(float nmean, float rstd, const float4& c0, const float4& c1, const float4& b0,
+                                          const float4& b1) {
+    const f32x2 nm = pk2(nmean, nmean), rs = pk2(rstd, rstd);
+    v[0] = fma2(rs, fma2(nm, pk2(c0.x, c0.y), v[0]), pk2(b0.x, b0.y));
+    v[1] = fma2(rs, fma2(nm, pk2(c0.z, c0.w), v[1]), pk2(b0.z, b0.w));
+    v[2] = fma2(rs, fma2(nm, pk2(c1.x, c1.y), v[2]), pk2(b1.x, b1.y));
+    v[3] = fma2(rs, fma2(nm, pk2(c1.z, c1.w), v[3]), pk2(b1.z, b1.w));
+  }
+  __device__ __forceinline__ void add_bias(const float4& b0, const float4& b1) {
+    v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
+    v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
+  }
+  __device__ __forceinline__ void add8(const float4& q0, const float4& q1) { add_bias(q0, q1); }
+  __device__ __forceinline__ void gelu_erf_() {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
+  }
+  __device__ __forceinline__ void gelu_tanh_() {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a, b;
+      upk2(v[j], a, b);
+      v[j] = pk2(gelu_tanh(a), gelu_tanh(b));
+    }
+  }
+  __device__ __forceinline__ void scale(float g) {
+    const f32x2 gg = pk2(g, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], gg);
+  }
+  // v = g * v + residual   (residual: 8 values of the activation dtype in 4 words)
+  template <typename T>
+  __device__ __forceinline__ void residual(float g, const uint32_t* rq) {
+    const f32x2 gg = pk2(g, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 r = Pack2<T>::unpack(rq[j]);
+      v[j] = fma2(gg, v[j], pk2(r.x, r.y));
+    }
+  }
+  template <typename T>
+  __device__ __forceinline__ void pack(uint32_t* oq) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a, b;
+      upk2(v[j], a, b);
+      oq[j] = Pack2<T>::pack(a, b);
+    }
+  }
+};
+
 // nearest-neighbour source index, identical arithmetic to F.interpolate(mode="nearest"):
 // scale = float(in)/out ; src = min(floor(dst*scale), in-1)
 __device__ __forceinline__ int time_index(int t_abs, int time_len, int time_total) {
@@ -221,6 +334,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                     const GemmParams p) {
   using L = SmemLayout<BN, CG, EW, TS>;
+  SF_GTL(const unsigned long long tl_entry = gtimer();)
   constexpr int kStages = L::kStages;
   constexpr int kTileM = kBM * CG;
   constexpr bool kLnCapable = (EPI == kEpiBias || EPI == kEpiAct);
@@ -324,7 +438,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
   // PDL: everything above overlapped the tail of the previous kernel; from here on we read its output
+  SF_GTL(const unsigned long long tl_prologue = gtimer();)
   griddep_wait();
+  SF_GTL(const unsigned long long tl_dep = gtimer();)
   griddep_launch_dependents();
 
   const GemmEpilogue& e = p.epi;
@@ -450,6 +566,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      SF_GTL(unsigned long long tl_first = 0;)
       for (TileWalk w(p.M, p.N, kTileM, BN, 1, worker, num_workers); w.valid(); w.next(), ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -458,6 +575,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          SF_GTL(if (kb == 0 && it == 0) tl_first = gtimer();)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
@@ -478,6 +596,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         // accumulator complete -> epilogue warps (of both CTAs)
         if constexpr (CG == 2) umma_commit_cg2_mc(&tmem_full[acc], 0x3); else umma_commit(&tmem_full[acc]);
+        SF_GTL(if (it == 0 && blockIdx.x == 0 && p.M < 1024) printf("gemm N=%d K=%d epi=%d: prologue +%llu dep_wait +%llu first_stage +%llu mma issued +%llu ns\n", p.N, p.K, EPI, tl_prologue - tl_entry, tl_dep - tl_entry, tl_first - tl_entry, gtimer() - tl_entry);)
       }
     }
     __syncwarp();
@@ -689,9 +808,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t ob[kCW / 2];
 #pragma unroll
           for (int g = 0; g < kCW / 8; ++g) {  // groups of 8 columns
-            float vv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) vv[j] = __uint_as_float(raw[h][g * 8 + j]);
+            Epi8 x8;                                 // packed pairs: see f32x2 above
+            x8.load(&raw[h][g * 8]);
             const float4 b0 = lds128f(bias_u + (c * kCW + g * 8) * 4);
             const float4 b1 = lds128f(bias_u + (c * kCW + g * 8 + 4) * 4);
             bool did_ln = false;
@@ -699,43 +817,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (ln) {
                 const float4 c0 = lds128f(csum_u + (c * kCW + g * 8) * 4);
                 const float4 c1 = lds128f(csum_u + (c * kCW + g * 8 + 4) * 4);
-                vv[0] = fmaf(rstd, fmaf(nmean, c0.x, vv[0]), b0.x); vv[1] = fmaf(rstd, fmaf(nmean, c0.y, vv[1]), b0.y);
-                vv[2] = fmaf(rstd, fmaf(nmean, c0.z, vv[2]), b0.z); vv[3] = fmaf(rstd, fmaf(nmean, c0.w, vv[3]), b0.w);
-                vv[4] = fmaf(rstd, fmaf(nmean, c1.x, vv[4]), b1.x); vv[5] = fmaf(rstd, fmaf(nmean, c1.y, vv[5]), b1.y);
-                vv[6] = fmaf(rstd, fmaf(nmean, c1.z, vv[6]), b1.z); vv[7] = fmaf(rstd, fmaf(nmean, c1.w, vv[7]), b1.w);
+                x8.ln_fold(nmean, rstd, c0, c1, b0, b1);
                 did_ln = true;
               }
             }
-            if (!did_ln) {
-              vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-              vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-            }
+            if (!did_ln) x8.add_bias(b0, b1);
             if constexpr (EPI == kEpiAct) {
-              if (e.act == kActGeluErf) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
-              }
+              if (e.act == kActGeluErf) x8.gelu_erf_();
+              else x8.gelu_tanh_();
             }
             if constexpr (EPI == kEpiResidual) {
-              const uint32_t* rq = &rb[g * 4];
-              const float2 r0 = Pack2<T>::unpack(rq[0]), r1 = Pack2<T>::unpack(rq[1]);
-              const float2 r2 = Pack2<T>::unpack(rq[2]), r3 = Pack2<T>::unpack(rq[3]);
-              vv[0] = fmaf(gscale, vv[0], r0.x); vv[1] = fmaf(gscale, vv[1], r0.y);
-              vv[2] = fmaf(gscale, vv[2], r1.x); vv[3] = fmaf(gscale, vv[3], r1.y);
-              vv[4] = fmaf(gscale, vv[4], r2.x); vv[5] = fmaf(gscale, vv[5], r2.y);
-              vv[6] = fmaf(gscale, vv[6], r3.x); vv[7] = fmaf(gscale, vv[7], r3.y);
+              x8.template residual<T>(gscale, &rb[g * 4]);
             } else if constexpr (EPI == kEpiBias) {
-              if (e.gate) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] *= gscale;
-              }
+              if (e.gate) x8.scale(gscale);
             }
             uint32_t* oq = &ob[g * 4];
-            oq[0] = Pack2<T>::pack(vv[0], vv[1]); oq[1] = Pack2<T>::pack(vv[2], vv[3]);
-            oq[2] = Pack2<T>::pack(vv[4], vv[5]); oq[3] = Pack2<T>::pack(vv[6], vv[7]);
+            x8.template pack<T>(oq);
             if constexpr (kStatsCapable) {
               if (want_stats) {   // statistics of the values as stored (rounded), what the next GEMM multiplies
                 const float2 q0 = Pack2<T>::unpack(oq[0]), q1 = Pack2<T>::unpack(oq[1]);
@@ -867,6 +964,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float st1 = 0.f, st2 = 0.f;   // partial (sum, sumsq) of this row's output columns
 
       mbar_wait(&tmem_full[acc], acc_phase);
+      SF_GTL(const unsigned long long tl_acc = gtimer();)
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
                               colgrp * kColsPerWarp;
@@ -896,9 +994,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t ob[kPieces][8];
 #pragma unroll
           for (int g = 0; g < kCW / 8; ++g) {  // groups of 8 columns
-            float vv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) vv[j] = __uint_as_float(raw[h][g * 8 + j]);
+            Epi8 x8;                                 // packed pairs: see f32x2 above
+            x8.load(&raw[h][g * 8]);
             const float4 b0 = lds128f(bias_u + (c * kCW + g * 8) * 4);
             const float4 b1 = lds128f(bias_u + (c * kCW + g * 8 + 4) * 4);
             bool did_ln = false;
@@ -906,58 +1003,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (ln) {
                 const float4 c0 = lds128f(csum_u + (c * kCW + g * 8) * 4);
                 const float4 c1 = lds128f(csum_u + (c * kCW + g * 8 + 4) * 4);
-                vv[0] = fmaf(rstd, fmaf(nmean, c0.x, vv[0]), b0.x); vv[1] = fmaf(rstd, fmaf(nmean, c0.y, vv[1]), b0.y);
-                vv[2] = fmaf(rstd, fmaf(nmean, c0.z, vv[2]), b0.z); vv[3] = fmaf(rstd, fmaf(nmean, c0.w, vv[3]), b0.w);
-                vv[4] = fmaf(rstd, fmaf(nmean, c1.x, vv[4]), b1.x); vv[5] = fmaf(rstd, fmaf(nmean, c1.y, vv[5]), b1.y);
-                vv[6] = fmaf(rstd, fmaf(nmean, c1.z, vv[6]), b1.z); vv[7] = fmaf(rstd, fmaf(nmean, c1.w, vv[7]), b1.w);
+                x8.ln_fold(nmean, rstd, c0, c1, b0, b1);
                 did_ln = true;
               }
             }
-            if (!did_ln) {
-              vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-              vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-            }
+            if (!did_ln) x8.add_bias(b0, b1);
             if constexpr (EPI == kEpiAct) {
-              if (e.act == kActGeluErf) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] = gelu_tanh(vv[j]);
-              }
+              if (e.act == kActGeluErf) x8.gelu_erf_();
+              else x8.gelu_tanh_();
             }
             if constexpr (EPI == kEpiEmbed) {
               const int col = col0 + g * 8;
-              if (pos_row && row_ok && col < p.N) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(pos_row + col));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(pos_row + col + 4));
-                vv[0] += q0.x; vv[1] += q0.y; vv[2] += q0.z; vv[3] += q0.w;
-                vv[4] += q1.x; vv[5] += q1.y; vv[6] += q1.z; vv[7] += q1.w;
-              }
-              if (time_row && row_ok && col < p.N) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(time_row + col));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(time_row + col + 4));
-                vv[0] += q0.x; vv[1] += q0.y; vv[2] += q0.z; vv[3] += q0.w;
-                vv[4] += q1.x; vv[5] += q1.y; vv[6] += q1.z; vv[7] += q1.w;
-              }
+              if (pos_row && row_ok && col < p.N)
+                x8.add8(__ldg(reinterpret_cast<const float4*>(pos_row + col)), __ldg(reinterpret_cast<const float4*>(pos_row + col + 4)));
+              if (time_row && row_ok && col < p.N)
+                x8.add8(__ldg(reinterpret_cast<const float4*>(time_row + col)), __ldg(reinterpret_cast<const float4*>(time_row + col + 4)));
             }
             if constexpr (EPI == kEpiResidual) {
-              const uint32_t* rq = &rbuf[h][g >> 1][(g & 1) * 4];
-              const float2 r0 = Pack2<T>::unpack(rq[0]), r1 = Pack2<T>::unpack(rq[1]);
-              const float2 r2 = Pack2<T>::unpack(rq[2]), r3 = Pack2<T>::unpack(rq[3]);
-              vv[0] = fmaf(gscale, vv[0], r0.x); vv[1] = fmaf(gscale, vv[1], r0.y);
-              vv[2] = fmaf(gscale, vv[2], r1.x); vv[3] = fmaf(gscale, vv[3], r1.y);
-              vv[4] = fmaf(gscale, vv[4], r2.x); vv[5] = fmaf(gscale, vv[5], r2.y);
-              vv[6] = fmaf(gscale, vv[6], r3.x); vv[7] = fmaf(gscale, vv[7], r3.y);
+              x8.template residual<T>(gscale, &rbuf[h][g >> 1][(g & 1) * 4]);
             } else if constexpr (EPI == kEpiBias) {
-              if (e.gate) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] *= gscale;
-              }
+              if (e.gate) x8.scale(gscale);
             }
             uint32_t* oq = &ob[g >> 1][(g & 1) * 4];
-            oq[0] = Pack2<T>::pack(vv[0], vv[1]); oq[1] = Pack2<T>::pack(vv[2], vv[3]);
-            oq[2] = Pack2<T>::pack(vv[4], vv[5]); oq[3] = Pack2<T>::pack(vv[6], vv[7]);
+            x8.template pack<T>(oq);
             if constexpr (kStatsCapable) {
               if (want_stats) {   // statistics of the values as stored (rounded), what the next GEMM multiplies
                 const float2 q0 = Pack2<T>::unpack(oq[0]), q1 = Pack2<T>::unpack(oq[1]);
@@ -983,6 +1051,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (CG == 2) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
         mbar_arrive(&aux_empty[acc]);
       }
+      SF_GTL(if (it == 0 && blockIdx.x == 0 && warp == 4 && lane == 0 && p.M < 1024) printf("gemm N=%d K=%d epi=%d: acc ready +%llu epilogue done +%llu ns\n", p.N, p.K, EPI, tl_acc - tl_entry, gtimer() - tl_entry);)
     }
   }
 
