@@ -90,7 +90,11 @@ uint64_t sf_launch_count(void);
  * a context-owned one, forked / joined with events) so that one half's kernel fill and drain overlap the other
  * half's steady state; 0 single stream; -1 the default (SF_DUAL_STREAM environment variable, off: measured
  * no gain on B200, 19.5 k vs 19.6 k frames/s at cfg2).  Profiling
- * modes, hidden-state / attention outputs, the KV cache and stream capture always use the single-stream schedule. */
+ * modes, hidden-state / attention outputs, the KV cache and stream capture always use the single-stream schedule.
+ * "spatial_row": kernel choice of the spatial attention at 193..200 tokens per frame (224 x 224): 1 the kernel that
+ * keeps whole score rows in registers, 0 the general two-pass tcgen05 kernel, -1 the default (SF_SPATIAL_ROW, on).
+ * "decode_tma": streaming decode kernel: 1 TMA-staged histories + mma.sync, 0 register-direct FMA kernel, -1 the
+ * default (SF_DECODE_TMA, off). */
 int sf_set_option(const char* name, int value);
 
 /* In-situ profiling: when enabled every kernel launch is bracketed by CUDA events on its stream.

@@ -1519,6 +1519,9 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
   return check_launch("temporal_attention");
 }
 
+int g_decode_tma_opt = -1;
+void set_decode_tma(int on) { g_decode_tma_opt = on; }
+
 bool temporal_decode_supported(int Tcap, int Tq) {
   static const bool on = [] { const char* e = getenv("SF_TEMPORAL_DECODE"); return !(e && e[0] == '0'); }();
   return on && Tq == 1 && Tcap <= kDecMaxRows && Tcap >= 1;
@@ -1561,7 +1564,8 @@ int temporal_decode(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv,
   ProfScope ps(stream, kProfTemporalAttn, 4.0 * sites * heads * static_cast<double>(seen + 1) * kHd,
                2.0 * sites * heads * kHd * (5.0 + 2.0 * seen));
   // SF_DECODE_TMA=1 selects the TMA-ring / mma.sync kernel; the default is the register-direct kernel
-  static const bool use_tma = [] { const char* e = getenv("SF_DECODE_TMA"); return e && e[0] == '1'; }();
+  static const bool tma_env = [] { const char* e = getenv("SF_DECODE_TMA"); return e && e[0] == '1'; }();
+  const bool use_tma = g_decode_tma_opt < 0 ? tma_env : g_decode_tma_opt != 0;
   if (!use_tma && (ld_qkv % 8 == 0) && (ld_out % 8 == 0) && (reinterpret_cast<uintptr_t>(qkv) % 16 == 0) &&
       (reinterpret_cast<uintptr_t>(out) % 16 == 0)) {
     long blocks = (a.tasks + 7) / 8;

@@ -655,6 +655,9 @@ int make_frame_map(CUtensorMap* map, int dtype, const void* base, int ld, int nc
 
 }  // namespace
 
+int g_spatial_row_opt = -1;
+void set_spatial_row(int on) { g_spatial_row_opt = on; }
+
 bool spatial_attention_tc_supported(int ld_qkv, int S) {
   return S >= 1 && S <= kMaxKeys && (ld_qkv % 8 == 0);
 }
@@ -677,7 +680,8 @@ int spatial_attention_tc(cudaStream_t stream, int dtype, const void* qkv, int ld
   const int grid = a.items < num_sms() ? a.items : num_sms();
   // 224x224 frames take the row-in-registers kernel (SF_SPATIAL_ROW=0 forces the general one); SF_SPATIAL_SKEW = start
   // offset of tile 1 in cycles.
-  static const bool row_on = [] { const char* e = getenv("SF_SPATIAL_ROW"); return !(e && e[0] == '0'); }();
+  static const bool row_env = [] { const char* e = getenv("SF_SPATIAL_ROW"); return !(e && e[0] == '0'); }();
+  const bool row_on = g_spatial_row_opt < 0 ? row_env : g_spatial_row_opt != 0;
   static const int skew = [] { const char* e = getenv("SF_SPATIAL_SKEW"); return e ? atoi(e) : kDefaultSkew; }();
   const bool row = row_on && S > (kRowOcts - 1) * 8 && S <= kRowOcts * 8 && ld_out % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(out) & 15) == 0;

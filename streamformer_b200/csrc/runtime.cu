@@ -913,6 +913,8 @@ int sf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_chain") == 0) { set_gemm_chain(value); return 0; }
   if (name && strcmp(name, "stream_graph") == 0) { g_stream_graph_opt = value; return 0; }
   if (name && strcmp(name, "dual_stream") == 0) { g_dual_stream_opt = value; return 0; }
+  if (name && strcmp(name, "spatial_row") == 0) { set_spatial_row(value); return 0; }
+  if (name && strcmp(name, "decode_tma") == 0) { set_decode_tma(value); return 0; }
   set_error("sf_set_option: unknown option '%s'", name ? name : "(null)");
   return SF_ERR_INVALID;
 }

@@ -77,6 +77,8 @@ struct GemmCall {
 };
 bool gemm_chain_supported(int dtype, const GemmCall* calls, int n);
 void set_gemm_chain(int on);   // -1: environment default (SF_GEMM_CHAIN, off), 0 / 1: force
+void set_spatial_row(int on);  // -1: environment default (SF_SPATIAL_ROW, on): row-in-registers spatial kernel at S = 196
+void set_decode_tma(int on);   // -1: environment default (SF_DECODE_TMA, off): TMA-ring / mma.sync streaming decode kernel
 int gemm_chain_stats_parts(const GemmCall* calls, int n, int N);
 size_t gemm_chain_counter_bytes(int M);
 int gemm_chain(cudaStream_t stream, int dtype, const GemmCall* calls, int n, void* counters);

@@ -301,11 +301,20 @@ def test_temporal_attention_kv_cache(Tnew, steps):
         _close(out, ref, torch.bfloat16, f"kv-cache step {s}", scale=2.0)
 
 
+@pytest.fixture(params=["direct", "tma_ring"])
+def decode_kernel(request):
+    """Both streaming decode kernels: the register-direct default and the TMA-ring / mma.sync one."""
+    from streamformer_b200 import _native as N
+    N.set_option("decode_tma", 1 if request.param == "tma_ring" else 0)
+    yield request.param
+    N.set_option("decode_tma", -1)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("sites,cap,steps", [(784, 64, 64), (61, 96, 96), (5, 8, 8), (3, 33, 33)])
-def test_temporal_decode_kernel(dtype, sites, cap, steps):
-    """Streaming decode kernel (bulk-copy staged histories, fused append): every step equals the matching row of
-    the one-shot causal attention; the cache it leaves behind equals what kv_append writes; ring depths 8 -> 2."""
+def test_temporal_decode_kernel(dtype, sites, cap, steps, decode_kernel):
+    """Streaming decode kernels (history straight into registers / bulk-copy staged, fused append): every step equals
+    the matching row of the one-shot causal attention; the cache it leaves behind equals what kv_append writes."""
     ops = _ops()
     g = torch.Generator(device="cpu").manual_seed(17)
     H, D = 12, 768
@@ -327,9 +336,18 @@ def test_temporal_decode_kernel(dtype, sites, cap, steps):
         ops.temporal_decode(qkv_all[:, 0].contiguous(), kc, vc, sites, H, cap, 0.125)
 
 
+@pytest.fixture(params=["row", "general"])
+def spatial_kernel(request):
+    """Both tcgen05 spatial kernels at S = 196: rows in registers (default) and the general two-pass one."""
+    from streamformer_b200 import _native as N
+    N.set_option("spatial_row", 1 if request.param == "row" else 0)
+    yield request.param
+    N.set_option("spatial_row", -1)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("frames,S", [(16, 196), (3, 49), (2, 392), (1, 64), (2, 1)])
-def test_spatial_attention(dtype, frames, S):
+@pytest.mark.parametrize("frames,S", [(16, 196), (3, 49), (2, 392), (1, 64), (2, 1), (5, 193), (40, 200)])
+def test_spatial_attention(dtype, frames, S, spatial_kernel):
     ops = _ops()
     g = torch.Generator(device="cpu").manual_seed(16)
     H, D = 12, 768
@@ -343,7 +361,7 @@ def test_spatial_attention(dtype, frames, S):
 
 
 @pytest.mark.parametrize("B,T,S", [(2, 16, 196), (1, 6, 196), (3, 5, 49), (4, 1, 196), (1, 24, 64)])
-def test_spatial_attention_in_place_layout(B, T, S):
+def test_spatial_attention_in_place_layout(B, T, S, spatial_kernel):
     """Frames read in place from the residual stream's (b,n,t) row order (row stride T), outputs
     written back in the same order: must equal the contiguous-frame result on permuted rows."""
     ops = _ops()
