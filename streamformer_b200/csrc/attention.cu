@@ -536,6 +536,7 @@ temporal_decode_direct_kernel(const TemporalArgs a, T* __restrict__ kc, T* __res
     const uint4 q4 = *reinterpret_cast<const uint4*>(row);
     const uint4 knew = *reinterpret_cast<const uint4*>(row + D);
     const uint4 vnew = *reinterpret_cast<const uint4*>(row + 2 * D);
+    if (task != task0) load_batch(task, 0);   // requested before anything waits on the row words above
     float qf[8];
     {
       const float2 q0 = Pack2<T>::unpack(q4.x), q1 = Pack2<T>::unpack(q4.y), q2 = Pack2<T>::unpack(q4.z), q3 = Pack2<T>::unpack(q4.w);
@@ -549,7 +550,7 @@ temporal_decode_direct_kernel(const TemporalArgs a, T* __restrict__ kc, T* __res
     float m_run = -INFINITY, l_part = 0.f;
     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int j0 = 0; j0 <= seen; j0 += 32) {
-      if (j0 > 0 || task != task0) load_batch(task, j0);
+      if (j0 > 0) load_batch(task, j0);
       float sc[8];
       float bm = -INFINITY;
 #pragma unroll

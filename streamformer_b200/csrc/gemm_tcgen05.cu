@@ -628,14 +628,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // Issue every global load of the tile first (bias / column-sum slices and all row-statistics
       // partials of the 128 rows), then wait for the stage: one memory round trip per tile instead
       // of one per row group — this warp must never be slower than the epilogue it feeds.
-      constexpr int kVec = BN / 4 / 32;                 // float4 per lane per table (2 for BN=256, 1 for 128)
+      constexpr int kVec = BN >= 128 ? BN / 4 / 32 : 1; // float4 per lane per table (2 for BN=256, 1 for 128; BN=64: lanes 0-15)
       float4 b4[kVec], c4[kVec];
 #pragma unroll
       for (int v = 0; v < kVec; ++v) {
         const int col = n0 + (v * 32 + lane) * 4;
         b4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         c4[v] = b4[v];
-        if (col < p.N) {
+        if (col < p.N && (v * 32 + lane) * 4 < BN) {
           if (e.bias) b4[v] = __ldg(reinterpret_cast<const float4*>(e.bias + col));
           if (ln) c4[v] = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + col));
         }
@@ -684,8 +684,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t aux_u = smem_u32(smem + L::kAuxOffset + st * L::kAuxBytesPerStage);
 #pragma unroll
       for (int v = 0; v < kVec; ++v) {
-        sts128f(aux_u + L::kAuxBias + (v * 32 + lane) * 16, b4[v]);
-        if constexpr (kLnCapable) sts128f(aux_u + L::kAuxColsum + (v * 32 + lane) * 16, c4[v]);
+        if ((v * 32 + lane) * 4 < BN) {
+          sts128f(aux_u + L::kAuxBias + (v * 32 + lane) * 16, b4[v]);
+          if constexpr (kLnCapable) sts128f(aux_u + L::kAuxColsum + (v * 32 + lane) * 16, c4[v]);
+        }
       }
       if constexpr (kLnCapable) {
         if (ln) {
@@ -1203,7 +1205,7 @@ int launch_gemm(cudaStream_t stream, int dtype, const void* A, int lda, const vo
 
 // Tile shape for an M x N output: 0 -> 256 x 256 on CTA pairs (cta_group::2: half the B traffic per
 // CTA) when that fills the machine, 1 -> 128 x 256 single-CTA tiles, 2 -> 128 x 128 for small
-// problems (more CTAs in flight).  SF_GEMM_MODE=1 forces single-CTA tiles (debug / A-B comparison).
+// problems (more CTAs in flight), 3 -> 128 x 64 for problems that leave even those tiles on under half the SMs.  SF_GEMM_MODE=1 forces single-CTA tiles (debug / A-B comparison).
 int pick_shape(int M, int N) {
   static const int mode = env_int("SF_GEMM_MODE", 0);
   const int m_tiles = (M + kBM - 1) / kBM;
@@ -1211,6 +1213,11 @@ int pick_shape(int M, int N) {
   const int n_tiles = (N + 255) / 256;
   if (mode != 1 && N >= 256 && m_tiles2 * n_tiles >= num_sms() / 2) return 0;
   if (N >= 256 && m_tiles * n_tiles >= num_sms()) return 1;
+  // 3 -> 128 x 64 tiles (four epilogue warps): streaming steps (M = 784) leave an N = 768 GEMM with 42 tiles of
+  // 128 x 128 on 148 SMs, each a load -> MMA -> epilogue chain of ~6 us (12 us at K = 3072); half-width tiles double the
+  // CTAs and halve the weight bytes, the MMA time and the epilogue of each.  SF_GEMM_BN64=0 disables.
+  static const bool bn64 = env_int("SF_GEMM_BN64", 1) != 0;
+  if (bn64 && m_tiles * ((N + 127) / 128) < num_sms() / 2 && m_tiles * ((N + 63) / 64) <= num_sms()) return 3;
   return 2;
 }
 // Epilogue warps: 16 (four per scheduler, 16-column chunks) for the GELU epilogue, whose MUFU/FMA
@@ -1234,6 +1241,9 @@ int dispatch_shape(cudaStream_t stream, int dtype, const void* A, int lda, const
       if (pick_epi_warps(EPI, p.epi) == 16) return launch_gemm<T, 256, 2, EPI, 16, true>(stream, dtype, A, lda, W, ldw, p);
       return launch_gemm<T, 256, 2, EPI, 8, true>(stream, dtype, A, lda, W, ldw, p);
     }
+  }
+  if constexpr (EPI != kEpiAct) {
+    if (shape == 3 && pick_epi_warps(EPI, p.epi) == 8) return launch_gemm<T, 64, 1, EPI, 4, false>(stream, dtype, A, lda, W, ldw, p);
   }
   if (pick_epi_warps(EPI, p.epi) == 16) {
     switch (shape) {
@@ -1778,8 +1788,9 @@ int gemm_stats_parts(int M, int N) {
   // stats_out comes from the residual / embed epilogues, which run with 8 epilogue warps unless forced
   static const int forced = env_int("SF_GEMM_EW", 0);
   const int ew = forced == 16 ? 16 : 8;
-  const int bn = pick_shape(M, N) == 2 ? 128 : 256;
-  const int cols_per_part = bn / (ew / 4);
+  const int shape = pick_shape(M, N);
+  // 128-wide tiles / 8 warps and 64-wide tiles / 4 warps both leave one partial per 64 columns
+  const int cols_per_part = (shape == 3 && ew == 8) ? 64 : (shape >= 2 ? 128 : 256) / (ew / 4);
   return (N + cols_per_part - 1) / cols_per_part;
 }
 
