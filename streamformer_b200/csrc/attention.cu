@@ -789,59 +789,106 @@ spatial_probs_kernel(const T* __restrict__ qkv, long ld_in, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------- pooling probe
-// one warp per (frame, head): scores over S keys against a fixed fp32 query, softmax, weighted V sum
+// One CTA per (frame, head): scores of the S keys against a fixed fp32 query, softmax, weighted V sum.  The four
+// warps take a quarter of the keys each; lane = (r = lane / 8, c = lane % 8) reads 16-byte chunk c of rows
+// n0 + 4 i + r, so one load instruction fetches four whole 128-byte head slices and eight of them are in flight per
+// lane (round 1 walked the S value rows one dependent 4-byte load at a time: 28 us for the 48 tasks of a streaming
+// step).  Scores go through shared memory, row maxima / sums / the four partial outputs meet there too.
 constexpr int kPoolMaxS = 1024;
 template <typename T>
 __global__ void __launch_bounds__(128)
 pool_attn_kernel(const T* __restrict__ kv, long ld, const float* __restrict__ q, T* __restrict__ out,
                  long out_ld, int frames, int heads, int S) {
-  __shared__ float sc[4][kPoolMaxS];
+  __shared__ float sc[kPoolMaxS];
+  __shared__ float red[4][2];
+  __shared__ float part[4][kHd];
   griddep_wait();
   griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long task = static_cast<long>(blockIdx.x) * 4 + warp;
-  if (task >= static_cast<long>(frames) * heads) return;
+  const int r = lane >> 3, c = lane & 7;
+  const long task = blockIdx.x;
   const int h = static_cast<int>(task % heads);
   const long frame = task / heads;
   const int D = heads * kHd;
-  const T* kb = kv + frame * S * ld + h * kHd;
+  const T* kb = kv + frame * S * ld + h * kHd + c * 8;
   const T* vb = kb + D;
-  const float* qh = q + h * kHd;
+  float qf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qf[j] = __ldg(q + h * kHd + c * 8 + j);
+  const int per = (S + 3) >> 2;                 // keys per warp
+  const int n_lo = warp * per, n_hi = (n_lo + per < S) ? n_lo + per : S;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+  // pass 1: scores of this warp's keys, their maximum
   float mx = -INFINITY;
-  for (int n = lane; n < S; n += 32) {
-    const T* kr = kb + static_cast<long>(n) * ld;
-    float acc = 0.f;
+  for (int n0 = n_lo; n0 < n_hi; n0 += 32) {
+    uint4 kk[8];
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      const uint4 u = *reinterpret_cast<const uint4*>(kr + ch * 8);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + 4 * i + r;
+      kk[i] = n < n_hi ? *reinterpret_cast<const uint4*>(kb + static_cast<long>(n) * ld) : zero4;
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = Pack2<T>::unpack(w[j]);
-        acc += f.x * __ldg(qh + ch * 8 + 2 * j) + f.y * __ldg(qh + ch * 8 + 2 * j + 1);
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + 4 * i + r;
+      const float2 k0 = Pack2<T>::unpack(kk[i].x), k1 = Pack2<T>::unpack(kk[i].y), k2 = Pack2<T>::unpack(kk[i].z), k3 = Pack2<T>::unpack(kk[i].w);
+      float d = qf[0] * k0.x;
+      d = fmaf(qf[1], k0.y, d); d = fmaf(qf[2], k1.x, d); d = fmaf(qf[3], k1.y, d);
+      d = fmaf(qf[4], k2.x, d); d = fmaf(qf[5], k2.y, d); d = fmaf(qf[6], k3.x, d); d = fmaf(qf[7], k3.y, d);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      if (n < n_hi) {
+        if (c == 0) sc[n] = d;
+        mx = fmaxf(mx, d);
       }
     }
-    sc[warp][n] = acc;
-    mx = fmaxf(mx, acc);
   }
   mx = warp_max(mx);
+  if (lane == 0) red[warp][0] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0][0], red[1][0]), fmaxf(red[2][0], red[3][0]));
+
+  // pass 2: probabilities and the weighted value sum of this warp's keys
   float sum = 0.f;
-  for (int n = lane; n < S; n += 32) {
-    const float e = __expf(sc[warp][n] - mx);
-    sc[warp][n] = e;
-    sum += e;
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int n0 = n_lo; n0 < n_hi; n0 += 32) {
+    uint4 vv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + 4 * i + r;
+      vv[i] = n < n_hi ? *reinterpret_cast<const uint4*>(vb + static_cast<long>(n) * ld) : zero4;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + 4 * i + r;
+      const float pj = n < n_hi ? __expf(sc[n] - mx) : 0.f;
+      sum += pj;
+      const float2 v0 = Pack2<T>::unpack(vv[i].x), v1 = Pack2<T>::unpack(vv[i].y), v2 = Pack2<T>::unpack(vv[i].z), v3 = Pack2<T>::unpack(vv[i].w);
+      o[0] = fmaf(pj, v0.x, o[0]); o[1] = fmaf(pj, v0.y, o[1]); o[2] = fmaf(pj, v1.x, o[2]); o[3] = fmaf(pj, v1.y, o[3]);
+      o[4] = fmaf(pj, v2.x, o[4]); o[5] = fmaf(pj, v2.y, o[5]); o[6] = fmaf(pj, v3.x, o[6]); o[7] = fmaf(pj, v3.y, o[7]);
+    }
   }
-  sum = warp_sum(sum);
-  __syncwarp();
-  const float inv = 1.f / sum;
-  float o0 = 0.f, o1 = 0.f;  // lane owns dims 2*lane, 2*lane+1
-  for (int n = 0; n < S; ++n) {
-    const float p = sc[warp][n];
-    const float2 f = Pack2<T>::unpack(*reinterpret_cast<const uint32_t*>(vb + static_cast<long>(n) * ld + 2 * lane));
-    o0 += p * f.x;
-    o1 += p * f.y;
+  // fold the four row groups of the warp (lanes of one group hold the same probabilities), then the four warps
+  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    o[d] += __shfl_xor_sync(0xffffffffu, o[d], 8);
+    o[d] += __shfl_xor_sync(0xffffffffu, o[d], 16);
   }
-  *reinterpret_cast<uint32_t*>(out + frame * out_ld + h * kHd + 2 * lane) = Pack2<T>::pack(o0 * inv, o1 * inv);
+  if (r == 0) {
+#pragma unroll
+    for (int d = 0; d < 8; ++d) part[warp][c * 8 + d] = o[d];
+    if (c == 0) red[warp][1] = sum;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const float inv = 1.f / ((red[0][1] + red[1][1]) + (red[2][1] + red[3][1]));
+    const float a0 = ((part[0][2 * lane] + part[1][2 * lane]) + (part[2][2 * lane] + part[3][2 * lane])) * inv;
+    const float a1 = ((part[0][2 * lane + 1] + part[1][2 * lane + 1]) + (part[2][2 * lane + 1] + part[3][2 * lane + 1])) * inv;
+    *reinterpret_cast<uint32_t*>(out + frame * out_ld + h * kHd + 2 * lane) = Pack2<T>::pack(a0, a1);
+  }
 }
 
 // ------------------------------------------------------------------------------- pooling probe, collapsed
@@ -1788,8 +1835,9 @@ int pool_attention(cudaStream_t stream, int dtype, const void* kv, int ld_kv, co
   if (frames <= 0) return 0;
   if (S > kPoolMaxS) { set_error("pool_attention: S=%d exceeds %d", S, kPoolMaxS); return -1; }
   if (dtype != kBF16 && dtype != kF16) { set_error("pool_attention: dtype must be bf16/f16"); return -1; }
+  if ((ld_kv % 8) || (reinterpret_cast<uintptr_t>(kv) & 15)) { set_error("pool_attention: 16-byte aligned rows required"); return -1; }
   const long tasks = static_cast<long>(frames) * heads;
-  const long blocks = (tasks + 3) / 4;
+  const long blocks = tasks;
   ProfScope ps(stream, kProfPoolAttn, 4.0 * frames * heads * static_cast<double>(S) * kHd,
                2.0 * frames * heads * kHd * 2.0 * S);
   LaunchCfg lc(dim3(static_cast<unsigned>(blocks)), dim3(128), 0, stream);
