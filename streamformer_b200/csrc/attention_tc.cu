@@ -348,20 +348,23 @@ spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 // columns of its row with four tcgen05.ld, and computes the maximum, the exponentials, the row sum and the packed P
 // branch-free out of registers: one read of S, no cross-warp exchange, one dependent TMEM round trip per row.
 //
-//   warp 0      TMA producer
+//   warp 0 / 3  TMA producers: K | V into a ring of three stages (up to two items ahead), Q into one buffer per M
+//               tile (free again once the tile's S has retired)
 //   warp 1 / 2  MMA issuer of M tile 0 / 1: S -> (softmax) -> PV per item, each on its own barriers
 //   warps 4-7   softmax + read-out of M tile 0 (TMEM region 0: S/P at columns [0, 208), O apart at [416, 480) so that
 //               S of the next item only waits for PV, not for the read-out)
 //   warps 8-11  the same for M tile 1 (region 1: S/P at [208, 416), O in the dead score columns [336, 400))
 // The two tiles free-run; `skew` delays tile 1's first S so that its exponential phase falls into tile 0's
 // load / maximum / read-out phases (the MUFU pipe is the one resource both need at full rate).
-constexpr int kDefaultSkew = 3500;                              // cycles; sweep on B200: 0 -> 46.1 us, 2500 -> 44.2, 3500 -> 43.3
+constexpr int kDefaultSkew = 2000;                              // cycles; sweep on B200 (three K|V stages): 0 -> 44.8 us, 2000 -> 43.2, 3500 -> 45.5, 5000 -> 46.1
 constexpr int kRowOcts = 25;                                    // 8-column groups held per thread (200 columns)
 constexpr int kReg1Col = kMaxKeys;                              // region 1 starts right behind region 0's scores
 constexpr int kO0Col = 2 * kMaxKeys;                            // O of region 0
-constexpr int kSoftmaxRegs = 232, kControlRegs = 40;
+constexpr int kSoftmaxRegs = 232, kControlRegs = 40;   // 40 + 2 x 232 = 3 x 168: exactly the registers the CTA was launched with (more would block setmaxnreg.inc forever)
 constexpr int kHalfKSteps = 7;                                  // PV k-steps (16 keys each) issued after the first half of P
-constexpr int kSmemBytesRow = 2 * kStageBytes + 1024 + 8 * 4096 + 1024;   // + one 32 x 128 B output tile per softmax warp
+constexpr int kRowKvStages = 3;                                 // K | V operand stages (52 KB each)
+constexpr int kRowKvStageBytes = 2 * kKVTileBytes;
+constexpr int kSmemBytesRow = kRowKvStages * kRowKvStageBytes + 2 * kQTileBytes + 1024 + 8 * 4096 + 1024;   // + one 32 x 128 B output tile per softmax warp
 
 #ifdef SF_ATTN_TIMELINE
 #define SF_TL(...) __VA_ARGS__
@@ -382,9 +385,13 @@ spatial_attn_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* kv_full = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes);
-  uint64_t* kv_empty = kv_full + 2;
-  uint64_t* s_full = kv_empty + 2;
+  // shared memory: kRowKvStages x (K | V) stages, one Q buffer per M tile, barriers, one output tile per softmax warp
+  uint8_t* q_smem = smem + kRowKvStages * kRowKvStageBytes;
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(q_smem + 2 * kQTileBytes);
+  uint64_t* kv_empty = kv_full + kRowKvStages;
+  uint64_t* q_full = kv_empty + kRowKvStages;
+  uint64_t* q_empty = q_full + 2;
+  uint64_t* s_full = q_empty + 2;
   uint64_t* p_full = s_full + 2;
   uint64_t* o_full = p_full + 2;
   uint64_t* region_free = o_full + 2;
@@ -396,9 +403,13 @@ spatial_attn_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmO);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kRowKvStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 2);      // one commit per tile's issuer
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);        // the four softmax warps of the tile
       mbar_init(&p_half[i], 4);
@@ -423,25 +434,42 @@ spatial_attn_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   if (warp < 4) {
     setmaxnreg_dec<kControlRegs>();
     if (warp == 0) {
-      // ---------------------------------------------------------------- TMA producer
+      // ---------------------------------------------------------------- TMA producer, K / V: a ring of three stages
+      // runs up to two items ahead, so the two M tiles can stay half an item apart without waiting for operands
       if (elect_one_sync()) {
+        int st = 0;
+        uint32_t ph = 0;
         for (int i = 0; i < nitems; ++i) {
           const int item = blockIdx.x + i * gridDim.x;
-          const int st = i & 1;
-          const uint32_t ph = (i >> 1) & 1;
           const int frame = item / a.heads, h = item % a.heads;
           const int b = a.T_inner > 1 ? frame / a.T_inner : frame;
           const int t = a.T_inner > 1 ? frame % a.T_inner : 0;
           mbar_wait(&kv_empty[st], ph ^ 1);
-          uint8_t* base = smem + st * kStageBytes;
-          mbar_arrive_expect_tx(&kv_full[st], static_cast<uint32_t>(2 * kQTileBytes + 2 * a.SK * 128));
-          tma_load_4d(base, &tmQ, &kv_full[st], h * kHd, t, 0, b);
-          tma_load_4d(base + 2 * kQTileBytes, &tmKV, &kv_full[st], D + h * kHd, t, 0, b);
-          tma_load_4d(base + kQTileBytes, &tmQ, &kv_full[st], h * kHd, t, 128, b);
-          tma_load_4d(base + 2 * kQTileBytes + kKVTileBytes, &tmKV, &kv_full[st], 2 * D + h * kHd, t, 0, b);
+          uint8_t* base = smem + st * kRowKvStageBytes;
+          mbar_arrive_expect_tx(&kv_full[st], static_cast<uint32_t>(2 * a.SK * 128));
+          tma_load_4d(base, &tmKV, &kv_full[st], D + h * kHd, t, 0, b);
+          tma_load_4d(base + kKVTileBytes, &tmKV, &kv_full[st], 2 * D + h * kHd, t, 0, b);
+          if (++st == kRowKvStages) { st = 0; ph ^= 1; }
         }
       }
-    } else if (warp <= 2) {
+    } else if (warp == 3) {
+      // ---------------------------------------------------------------- TMA producer, Q: one buffer per M tile, free
+      // again as soon as the tile's S = Q K^T has retired
+      if (elect_one_sync()) {
+        for (int i = 0; i < nitems; ++i) {
+          const int item = blockIdx.x + i * gridDim.x;
+          const int frame = item / a.heads, h = item % a.heads;
+          const int b = a.T_inner > 1 ? frame / a.T_inner : frame;
+          const int t = a.T_inner > 1 ? frame % a.T_inner : 0;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            mbar_wait(&q_empty[r], (i & 1) ^ 1);
+            mbar_arrive_expect_tx(&q_full[r], kQTileBytes);
+            tma_load_4d(q_smem + r * kQTileBytes, &tmQ, &q_full[r], h * kHd, t, r * 128, b);
+          }
+        }
+      }
+    } else {
       // ---------------------------------------------------------------- MMA issuer of tile r
       const int r = warp - 1;
       if (elect_one_sync()) {
@@ -450,11 +478,13 @@ spatial_attn_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int ksteps_pv = a.SK / 16;
         const uint32_t d_s = tmem_base + (r ? kReg1Col : 0);
         const uint32_t d_o = tmem_base + (r ? kReg1Col + kOCol : kO0Col);
+        int st = 0;
+        uint32_t kv_ph = 0;
         for (int i = 0; i < nitems; ++i) {
-          const int st = i & 1;
           const uint32_t par = i & 1;
-          const uint32_t sbase = smem_u32(smem + st * kStageBytes);
-          mbar_wait(&kv_full[st], (i >> 1) & 1);
+          const uint32_t sbase = smem_u32(smem + st * kRowKvStageBytes);
+          mbar_wait(&kv_full[st], kv_ph);
+          mbar_wait(&q_full[r], par);
           if (r == 1 && i == 0 && ra.skew > 0) {      // de-phase the two tiles once the first operands have landed
             const long long t0 = clock64();
             while (clock64() - t0 < ra.skew) {}
@@ -464,12 +494,13 @@ spatial_attn_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           if (r == 0) mbar_wait(&o_full[0], par ^ 1);
           else mbar_wait(&region_free[1], par ^ 1);
           tc_fence_after();
-          const uint64_t dq = umma_desc_sw128_kmajor(sbase + r * kQTileBytes);
-          const uint64_t dk = umma_desc_sw128_kmajor(sbase + 2 * kQTileBytes);
+          const uint64_t dq = umma_desc_sw128_kmajor(smem_u32(q_smem + r * kQTileBytes));
+          const uint64_t dk = umma_desc_sw128_kmajor(sbase);
 #pragma unroll
           for (int k = 0; k < kHd / 16; ++k) umma_f16(d_s, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
           umma_commit(&s_full[r]);
-          const uint64_t dv = umma_desc_sw128_mnmajor(sbase + 2 * kQTileBytes + kKVTileBytes);
+          umma_commit(&q_empty[r]);     // the Q buffer is free for the next item
+          const uint64_t dv = umma_desc_sw128_mnmajor(sbase + kKVTileBytes);
           mbar_wait(&p_half[r], par);                 // P of keys 0 .. 111 is in tensor memory
           tc_fence_after();
 #pragma unroll
@@ -481,6 +512,7 @@ spatial_attn_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             umma_f16_ts(d_o, d_s + k * 8, dv + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, 1u);
           umma_commit(&o_full[r]);
           umma_commit(&kv_empty[st]);   // this tile's MMAs that read the stage's smem have retired
+          if (++st == kRowKvStages) { st = 0; kv_ph ^= 1; }
         }
       }
     }
@@ -495,7 +527,7 @@ spatial_attn_row_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t t_s = tmem_base + (r ? kReg1Col : 0) + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_o = tmem_base + (r ? kReg1Col + kOCol : kO0Col) + (static_cast<uint32_t>(quarter * 32) << 16);
     SF_TL(__shared__ int tlog[2 * 12 * 7]; long long tbase = 0;)
-    uint8_t* otile = smem + 2 * kStageBytes + 1024 + (warp - 4) * 4096;   // 1024-byte aligned: TMA's 128B swizzle
+    uint8_t* otile = q_smem + 2 * kQTileBytes + 1024 + (warp - 4) * 4096;   // 1024-byte aligned: TMA's 128B swizzle
     for (int i = 0; i < nitems; ++i) {
       const int item = blockIdx.x + i * gridDim.x;
       const uint32_t par = i & 1;

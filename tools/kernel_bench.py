@@ -44,7 +44,7 @@ def main():
     dev, dt = "cuda", torch.bfloat16
     S, D, I = 196, 768, 3072
     M = a.B * a.T * S
-    nrot = 4
+    nrot = int(os.environ.get("SF_KB_NROT", "4"))   # input sets the timed loop rotates over (1: L2-resident inputs)
     res = {}
 
     def gemm_case(name, Nn, K, **kw):
