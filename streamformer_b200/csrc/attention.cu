@@ -356,7 +356,11 @@ constexpr int kDecSlabBytes = 16 * 128;             // 16 rows x 64 two-byte ele
 constexpr int kDecMaxRows = 96;                     // frames incl. the new one
 constexpr int kDecMaxWarps = 12;
 constexpr int kDecSmem = kDecStaging + kDecMaxWarps * kDecMaxStages * 8 + 1024;
-inline int dec_warps(int Tcap) { return Tcap <= 64 ? 12 : 8; }
+inline int dec_warps(int Tcap) {
+  static const int forced = [] { const char* e = getenv("SF_DEC_WARPS"); return e ? atoi(e) : 0; }();   // tuning knob
+  if (forced >= 1 && forced <= kDecMaxWarps) return forced;
+  return Tcap <= 64 ? 12 : 8;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kDecMaxWarps * 32, 1)
