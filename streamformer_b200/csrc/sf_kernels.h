@@ -118,8 +118,9 @@ int temporal_attention(cudaStream_t stream, int dtype, const void* qkv, int ld_q
                        const void* vcache, int Tcap, void* out, int ld_out, int sites, int heads,
                        int Tq, int Tk, int q_off, int causal, float scale, const int* seen_dev = nullptr);
 
-// Streaming decode (Tq == 1 with a cache): kv_append + temporal_attention in one kernel, the (site, head)
-// histories staged by cp.async.bulk (attention.cu).  Supported for caches of up to 96 frames.
+// Streaming decode (Tq == 1 with a cache): kv_append + temporal_attention in one kernel (attention.cu): by default
+// the register-direct FMA kernel (histories global -> registers with 16-byte loads), with set_decode_tma(1) /
+// SF_DECODE_TMA=1 the TMA-ring + mma.sync kernel.  Supported for caches of up to 96 frames.
 bool temporal_decode_supported(int Tcap, int Tq);
 int temporal_decode(cudaStream_t stream, int dtype, const void* qkv, int ld_qkv, void* kcache, void* vcache, int Tcap,
                     void* out, int ld_out, int sites, int heads, int seen, float scale, const int* seen_dev = nullptr);
